@@ -1,0 +1,140 @@
+/*
+ * scpd.h -- C ABI of the B200-native batched successive-cancellation polar decoder.
+ *
+ * Drop-in boundary for the decode path of ydelomier/SC_Polar_decoder_HLS.  The reference has
+ * no function-call API: its decoder is SC_MODULE(my_module) (src/module/my_module.h:15-46)
+ * wired between wrapper_in / wrapper_out by sc_top_module (src/testbench/sc_top_module.h:146-160),
+ * and configured by macros (src/module/config.h, src/module/polar_parameters.h).  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions kept from the reference:
+ *   - LLRs: one signed 8-bit value per code bit, natural index order, positive <=> bit 0
+ *     (sc_bpsk.h:53), produced by the quantiser clamp(trunc(4y), -31, 31) (sc_quantizer.h:77-80);
+ *     any value in [-(2^(Q-1)-1), 2^(Q-1)-1] is accepted (Q = llr_bits).
+ *   - frozen table: N flags, 1 = information bit, 0 = frozen (Writer.h:86-93; my_module.h:92-95).
+ *   - output: the estimated CODEWORD x^ (what my_module streams out of bit_mem_1,
+ *     my_module.h:1859-1866), packed LSB-first: bit i of a frame is bit (i % 32) of word i / 32
+ *     (the PAR-bit words of wrapper_out.h:31-33 laid end to end).
+ *   - arithmetic: bit-exact with the reference for (format, llr_bits, par, extended):
+ *     shared/src/functions.h:48-347 (f, g, h), :354-866 (PAR-wide leaf decoders).
+ *
+ * All pointers named d_* are DEVICE pointers; h_* are host pointers.  Calls taking a stream are
+ * asynchronous on that stream.  A handle is bound to one device and is not thread-safe.
+ * There is no CPU fallback: every compute entry point fails with SCPD_E_CUDA if no device works.
+ */
+#ifndef SCPD_H
+#define SCPD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCPD_VERSION 100
+
+typedef enum {
+    SCPD_OK = 0,
+    SCPD_E_ARG = 1,         /* null pointer / bad size */
+    SCPD_E_CONFIG = 2,      /* N not a power of two, 2*PAR > N, K != popcount(flags), ... */
+    SCPD_E_UNSUPPORTED = 3, /* valid reference configuration this build has no kernel for */
+    SCPD_E_IO = 4,          /* file missing / unparsable */
+    SCPD_E_CUDA = 5,        /* CUDA runtime error (scpd_last_error() has the text) */
+    SCPD_E_NOMEM = 6
+} scpd_status;
+
+typedef enum { SCPD_FMT_CA2 = 0, SCPD_FMT_SIGMAG = 1 } scpd_format; /* config.h:11 CA2 / SIGMAG */
+
+/* Pruning: which proven-bit-identical node shortcuts the schedule may use.  None of them changes
+ * a single output bit w.r.t. plain SC (reference PRUNING_LEVEL 0); they only skip work. */
+typedef enum {
+    SCPD_PRUNE_NONE = 0, /* visit every node, as PRUNING_LEVEL 0 (config.h:16) */
+    SCPD_PRUNE_R0 = 1,   /* skip all-frozen subtrees */
+    SCPD_PRUNE_R0_R1 = 2 /* + all-information subtrees by hard decision when no input LLR is a
+                            CA2 zero (falls back to plain SC on that node otherwise) */
+} scpd_pruning;
+
+/* Replaces the compile-time macros of config.h:2-16 and polar_parameters.h:4-11. */
+typedef struct {
+    uint32_t n;        /* _NBITS                                  */
+    uint32_t k;        /* number of information bits (checked)    */
+    uint32_t par;      /* PAR: width of the leaf decoder          */
+    uint32_t llr_bits; /* LLR_BITS                                */
+    uint32_t format;   /* scpd_format                             */
+    uint32_t extended; /* EXTENDED                                */
+    uint32_t pruning;  /* scpd_pruning                            */
+    uint32_t reserved;
+} scpd_config;
+
+typedef struct scpd_decoder scpd_decoder; /* opaque; one per (device, configuration, frozen set) */
+
+/* ---- frozen-bit tables: Frozen_Bit_Generator/src/Writer.h:21-171 ---- */
+/* Frozen_Bit_Tab/FB_N*_K*.txt: "N\r\n0\r\n0\r\n" then channel indices, most reliable first
+ * (Writer.h:35-58).  Indices >= n are dropped, the first k survivors are information bits
+ * (Writer.h:64-93).  flags_out: n bytes. */
+int scpd_frozen_load_order(const char* path, uint32_t n, uint32_t k, uint8_t* flags_out);
+/* Generated_Frozen_Bit/frozen_n_*_k_*.txt: one line of n tokens 0|1 (Writer.h:95-105).
+ * k_out (optional) receives the number of ones. */
+int scpd_frozen_load_flags(const char* path, uint32_t n, uint8_t* flags_out, uint32_t* k_out);
+/* The "affect" file Writer.h:75-80 writes back: order restricted to indices < n. */
+int scpd_frozen_write_order(const char* path, uint32_t n, const uint32_t* order);
+/* Single-line flag file in the Generated_Frozen_Bit format. */
+int scpd_frozen_write_flags(const char* path, uint32_t n, const uint8_t* flags);
+/* polar_parameters.h exactly as Writer.h:110-162 emits it (en = "En" argument, main.cpp:29),
+ * so the HLS flow can still consume tables loaded here. */
+int scpd_write_polar_parameters(const char* path, uint32_t n, uint32_t par, int en,
+                                const uint8_t* flags);
+
+/* ---- decoder: SC_MODULE(my_module), my_module.h:15-46 ---- */
+/* FB port + do_prunning (my_module.h:61-166): ingest the table, build the device schedule. */
+int scpd_create(const scpd_config* cfg, const uint8_t* h_info_flags, int device,
+                scpd_decoder** out);
+void scpd_destroy(scpd_decoder* dec);
+/* e -> s ports (my_module.h:34-35): decode nframes frames.
+ * d_llr  : [nframes][n] int8, device.      d_xhat : [nframes][n/32] uint32, device. */
+int scpd_decode(scpd_decoder* dec, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat,
+                void* cuda_stream);
+/* Same through host buffers (pinned or pageable): H2D copy, decode, D2H copy, stream sync.
+ * This is the call a host-only caller such as the reference testbench would make. */
+int scpd_decode_host(scpd_decoder* dec, const int8_t* h_llr, size_t nframes, uint32_t* h_xhat);
+/* Information-bit estimate u^ = x^ * F^(x)n (extra; the reference outputs x^ only). */
+int scpd_extract_info(scpd_decoder* dec, const uint32_t* d_xhat, size_t nframes, uint32_t* d_uhat,
+                      void* cuda_stream);
+/* Introspection. */
+int scpd_get_config(const scpd_decoder* dec, scpd_config* out);
+/* Number of schedule operations and of f/g element updates per frame after pruning. */
+int scpd_schedule_stats(const scpd_decoder* dec, uint64_t* n_ops, uint64_t* n_fg_updates);
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+uint64_t scpd_launch_count(const scpd_decoder* dec);
+
+/* ---- testbench harness on the device: src/testbench/ ---- */
+/* sigma = 1/sqrt(2 R 10^(EbN0/10)), main.cpp:91-98 (the reference hard-codes R = 0.5). */
+float scpd_sigma(float ebn0_db, float rate);
+/* sc_xorshift128 (two streams, seed byte) -> sc_awgn (Box-Muller, 2 samples per draw) ->
+ * sc_bpsk + sc_adder -> sc_quantizer.  Frame f of the stream uses draws [f*n/2, (f+1)*n/2) of
+ * each generator, reached by GF(2) jump-ahead.  d_codeword: n bytes (0/1) shared by all frames
+ * if per_frame == 0, [nframes][n] if 1, or NULL for the all-zero codeword (sc_encoder.h:105-110).
+ * d_llr: [nframes][n] int8. */
+int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nframes, uint8_t seed,
+                          float sigma, const uint8_t* d_codeword, int per_frame, int8_t* d_llr,
+                          void* cuda_stream);
+/* sc_error_counter.h:68-125.  d_ref_words: packed reference codeword(s) ([n/32] shared or
+ * [nframes][n/32]) or NULL for all-zero.  d_counters (6 x uint64, accumulated, caller zeroes):
+ * [0] bit errors [1] frame errors [2] bits [3] frames [4],[5] as [0],[1] with the reference's
+ * 10-bit per-frame wrap (sc_uint<10> err, :70-71). */
+int scpd_count_errors(uint32_t n, size_t nframes, const uint32_t* d_xhat,
+                      const uint32_t* d_ref_words, int per_frame, uint64_t* d_counters,
+                      void* cuda_stream);
+/* Whole Monte-Carlo loop of src/testbench/main.cpp on the device: generate -> decode -> count,
+ * nframes frames starting at stream position first_frame, in batches; h_counters as above. */
+int scpd_run_ber(scpd_decoder* dec, float ebn0_db, float rate, uint64_t first_frame,
+                 uint64_t nframes, uint8_t seed, const uint8_t* h_codeword, uint64_t h_counters[6]);
+
+const char* scpd_last_error(void);
+const char* scpd_status_string(int status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCPD_H */

@@ -1,0 +1,41 @@
+"""Build libscpd.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libscpd.so")
+SOURCES = ["scpd_api.cu", "frozen_io.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _newest_source_mtime():
+    t = 0.0
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for fn in os.listdir(root):
+            t = max(t, os.path.getmtime(os.path.join(root, fn)))
+    return t
+
+
+def build_lib(force=False, verbose=False):
+    """Compile every CUDA source of the package into libscpd.so. Returns the library path."""
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        if os.path.exists(LIB):
+            return LIB  # GPU box without a toolkit: use the library that travelled with the snapshot
+        raise RuntimeError("nvcc not found and no prebuilt libscpd.so")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout)
+    if verbose:
+        print(r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force=True, verbose=True))

@@ -1,0 +1,130 @@
+// schedule.h -- the static SC tree walk, compiled once per frozen set on the host.
+//
+// The reference walks the tree with an FSM and two packed stacks (my_module.h:228-263, states
+// INIT/F/R/G/H; functions.h:11-37).  All frames of a batch share the frozen set, so here the walk
+// is a straight-line program ("schedule") of node operations that every warp executes in lock
+// step; do_prunning's node classification (my_module.h:96-154) happens here too, at build time.
+//
+// One op = one uint32:  [3:0] opcode  [8:4] level l (node size n = 2^l)  [9] nosat
+//                       [11:10] leaf flags  [31:12] offset o of the node in the frame.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#ifdef __CUDACC__
+#define SCPD_HD __host__ __device__
+#else
+#define SCPD_HD
+#endif
+
+namespace scpd {
+
+enum Op : uint32_t {
+    OP_END = 0,
+    OP_F = 1,      // alpha[l-1][i] = f(alpha[l][i], alpha[l][i+n/2])            F_STATE  :373-445
+    OP_G = 2,      // alpha[l-1][i] = g(alpha[l][i], alpha[l][i+n/2], beta[o+i]) G_STATE  :704-781
+    OP_G0 = 3,     // same with beta = 0 (left child all-frozen)
+    OP_H = 4,      // beta[o+i] ^= beta[o+n/2+i], i < n/2                        H_STATE  :903-932
+    OP_HCOPY = 5,  // beta[o+i]  = beta[o+n/2+i]   (left child all-frozen: 0 ^ x)
+    OP_R0 = 6,     // beta[o..o+n) = 0            (all-frozen node)
+    OP_R1 = 7,     // all-information node: hard decision, plain-SC fallback if an LLR is 0
+    OP_P2 = 8,     // two-bit terminal, Spec_P2 functions.h:367-384; leaf flags = (f0, f1)
+    OP_P1 = 9,     // one-bit terminal, Spec_P1 functions.h:355-364; leaf flag bit0 = f
+};
+
+SCPD_HD static inline uint32_t op_make(uint32_t opc, uint32_t level, uint32_t offset, uint32_t nosat = 0,
+                               uint32_t lf = 0) {
+    return opc | (level << 4) | (nosat << 9) | (lf << 10) | (offset << 12);
+}
+SCPD_HD static inline uint32_t op_code(uint32_t w) { return w & 15u; }
+SCPD_HD static inline uint32_t op_level(uint32_t w) { return (w >> 4) & 31u; }
+SCPD_HD static inline uint32_t op_nosat(uint32_t w) { return (w >> 9) & 1u; }
+SCPD_HD static inline uint32_t op_lf(uint32_t w) { return (w >> 10) & 3u; }
+SCPD_HD static inline uint32_t op_offset(uint32_t w) { return w >> 12; }
+
+struct ScheduleStats {
+    uint64_t n_ops = 0;
+    uint64_t n_f = 0;   // f element updates per frame
+    uint64_t n_g = 0;   // g element updates per frame
+    uint64_t n_r0 = 0;  // pruned all-frozen nodes
+    uint64_t n_r1 = 0;  // pruned all-information nodes
+};
+
+struct ScheduleBuilder {
+    int log2n, log2par, extended, pruning;
+    const uint8_t* flags;
+    std::vector<uint32_t> psum;  // prefix sums of flags
+    std::vector<uint32_t> ops;
+    ScheduleStats st;
+
+    uint32_t count(uint32_t o, uint32_t n) const { return psum[o + n] - psum[o]; }
+    // g of a node of size n is the un-saturated Function_G_ext iff the node lies inside the
+    // PAR-wide leaf decoder and EXTENDED == 1 (Spec_P*_ext, functions.h:413-438 ...).
+    uint32_t nosat(int l) const { return (extended && l <= log2par) ? 1u : 0u; }
+
+    void emit(int l, uint32_t o) {
+        const uint32_t n = 1u << l;
+        const uint32_t c = count(o, n);
+        if (pruning >= 1 && c == 0) {
+            ops.push_back(op_make(OP_R0, l, o));
+            st.n_r0++;
+            return;
+        }
+        if (l == 0) {  // only reachable when PAR == 1
+            ops.push_back(op_make(OP_P1, 0, o, 0, flags[o] & 1u));
+            return;
+        }
+        if (l == 1 && log2par >= 1) {
+            ops.push_back(op_make(OP_P2, 1, o, 0, (flags[o] & 1u) | ((flags[o + 1] & 1u) << 1)));
+            return;
+        }
+        if (pruning >= 2 && c == n) {
+            ops.push_back(op_make(OP_R1, l, o));
+            st.n_r1++;
+            return;
+        }
+        const uint32_t h = n >> 1;
+        const bool left_r0 = pruning >= 1 && count(o, h) == 0;
+        const bool right_r0 = pruning >= 1 && count(o + h, h) == 0;
+        if (left_r0) {
+            ops.push_back(op_make(OP_G0, l, o, nosat(l)));
+            st.n_g += h;
+            emit(l - 1, o + h);
+            ops.push_back(op_make(OP_HCOPY, l, o));
+            return;
+        }
+        ops.push_back(op_make(OP_F, l, o));
+        st.n_f += h;
+        emit(l - 1, o);
+        if (right_r0) {
+            ops.push_back(op_make(OP_R0, l - 1, o + h));
+            st.n_r0++;
+            return;
+        }
+        ops.push_back(op_make(OP_G, l, o, nosat(l)));
+        st.n_g += h;
+        emit(l - 1, o + h);
+        ops.push_back(op_make(OP_H, l, o));
+    }
+};
+
+// flags: n bytes, 1 = information bit.  Returns the op list terminated by OP_END.
+static inline std::vector<uint32_t> build_schedule(int log2n, int log2par, int extended, int pruning,
+                                                   const uint8_t* flags, ScheduleStats* stats) {
+    ScheduleBuilder b;
+    b.log2n = log2n;
+    b.log2par = log2par;
+    b.extended = extended;
+    b.pruning = pruning;
+    b.flags = flags;
+    const uint32_t n = 1u << log2n;
+    b.psum.assign(n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) b.psum[i + 1] = b.psum[i] + (flags[i] ? 1u : 0u);
+    b.emit(log2n, 0);
+    b.ops.push_back(op_make(OP_END, 0, 0));
+    b.st.n_ops = b.ops.size();
+    if (stats) *stats = b.st;
+    return b.ops;
+}
+
+}  // namespace scpd

@@ -1,0 +1,432 @@
+// scpd_api.cu -- C ABI (include/scpd.h): handle management, launch plumbing, testbench harness.
+// Host logic only; the kernels are in decode_*.cuh / harness.cuh.  No CPU decode path exists.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/scpd.h"
+#include "decode_generic.cuh"
+#include "harness.cuh"
+#include "internal.h"
+#include "schedule.h"
+
+namespace scpd {
+
+static thread_local std::string g_last_error;
+int set_error(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return set_error(SCPD_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(expr)                                   \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr); \
+    } while (0)
+
+// ---------------------------------------------------------------- xorshift128 jump matrices
+struct Bits128 {
+    uint32_t w[4];
+};
+static Bits128 xs_step(Bits128 s) {  // sc_xorshift128.h:78-85 on (x,y,z,w) = w[0..3]
+    uint32_t t = s.w[0];
+    t ^= t << 11;
+    t ^= t >> 8;
+    Bits128 r;
+    r.w[0] = s.w[1];
+    r.w[1] = s.w[2];
+    r.w[2] = s.w[3];
+    r.w[3] = s.w[3] ^ (s.w[3] >> 19) ^ t;
+    return r;
+}
+static Bits128 mat_apply(const std::vector<Bits128>& cols, const Bits128& v) {
+    Bits128 r = {{0, 0, 0, 0}};
+    for (int b = 0; b < 128; b++)
+        if ((v.w[b >> 5] >> (b & 31)) & 1u)
+            for (int k = 0; k < 4; k++) r.w[k] ^= cols[b].w[k];
+    return r;
+}
+static const std::vector<Bits128>& jump_table_host() {
+    static std::vector<Bits128> table;  // [64][128]
+    static std::once_flag once;
+    std::call_once(once, [] {
+        table.resize(64 * 128);
+        for (int b = 0; b < 128; b++) {
+            Bits128 e = {{0, 0, 0, 0}};
+            e.w[b >> 5] = 1u << (b & 31);
+            table[b] = xs_step(e);
+        }
+        for (int j = 1; j < 64; j++) {
+            std::vector<Bits128> prev(table.begin() + (j - 1) * 128, table.begin() + j * 128);
+            for (int b = 0; b < 128; b++) table[j * 128 + b] = mat_apply(prev, prev[b]);  // T^(2^j) = T^(2^(j-1)) squared
+        }
+    });
+    return table;
+}
+static std::mutex g_jt_mutex;
+static std::map<int, uint4*> g_jt_dev;
+static int jump_table_device(int device, XsJumpTable* out) {
+    std::lock_guard<std::mutex> lk(g_jt_mutex);
+    auto it = g_jt_dev.find(device);
+    if (it == g_jt_dev.end()) {
+        const auto& h = jump_table_host();
+        uint4* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(Bits128)));
+        CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(Bits128), cudaMemcpyHostToDevice));
+        it = g_jt_dev.emplace(device, d).first;
+    }
+    out->cols = it->second;
+    return SCPD_OK;
+}
+
+}  // namespace scpd
+
+using namespace scpd;
+
+struct scpd_decoder {
+    scpd_config cfg;
+    int device = 0;
+    int log2n = 0, log2par = 0;
+    uint32_t wpf = 1;
+    std::vector<uint32_t> sched_host;
+    ScheduleStats stats;
+    uint32_t* d_sched = nullptr;
+    // generic-kernel layout
+    int group = 32;  // lanes per frame pair
+    int warps_per_cta = 4;
+    uint32_t ls = 0, beta_in_smem = 1, sm_words_per_fp = 0;
+    unsigned long long ws_words_per_fp = 0;
+    size_t smem_bytes = 0;
+    int ctas_per_sm = 1, num_sms = 1;
+    uint32_t* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    // staging for scpd_decode_host / scpd_run_ber
+    int8_t* d_llr = nullptr;
+    uint32_t* d_xhat = nullptr;
+    size_t stage_frames = 0;
+    unsigned long long* d_counters = nullptr;
+    uint64_t launches = 0;
+};
+
+static const void* generic_kernel_ptr(int group) {
+    switch (group) {
+        case 8: return (const void*)sc_decode_generic_kernel<8>;
+        case 16: return (const void*)sc_decode_generic_kernel<16>;
+        default: return (const void*)sc_decode_generic_kernel<32>;
+    }
+}
+
+static int plan_layout(scpd_decoder* d) {
+    const char* env = std::getenv("SCPD_GROUP");
+    d->group = 32;
+    if (env) {
+        int g = std::atoi(env);
+        if (g == 8 || g == 16 || g == 32) d->group = g;
+    }
+    const int gpw = 32 / d->group;
+    const int fp_per_cta = d->warps_per_cta * gpw;
+    const size_t budget = 100 * 1024;  // two CTAs per SM
+    const size_t per_fp_words = budget / 4 / fp_per_cta;
+    const uint32_t n = d->cfg.n;
+    // largest ls <= log2n-1 whose alpha levels 0..ls fit
+    int ls = 0;
+    for (int l = 0; l <= d->log2n - 1; l++)
+        if ((size_t)(2u << l) <= per_fp_words) ls = l;
+    if (d->log2n == 1) ls = 0;
+    d->ls = (uint32_t)ls;
+    size_t words = (size_t)(2u << ls);
+    d->beta_in_smem = (words + 2 * d->wpf <= per_fp_words) ? 1u : 0u;
+    if (d->beta_in_smem) words += 2 * d->wpf;
+    d->sm_words_per_fp = (uint32_t)words;
+    d->smem_bytes = words * 4 * fp_per_cta;
+    const bool need_ws_alpha = (int)d->ls < d->log2n - 1;
+    d->ws_words_per_fp = (need_ws_alpha || !d->beta_in_smem) ? (unsigned long long)n + 2ull * d->wpf : 0ull;
+    const void* k = generic_kernel_ptr(d->group);
+    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, d->warps_per_cta * 32, d->smem_bytes));
+    if (occ < 1) return set_error(SCPD_E_CUDA, "decode kernel does not fit on an SM");
+    d->ctas_per_sm = occ;
+    return SCPD_OK;
+}
+
+extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int device, scpd_decoder** out) {
+    if (!cfg || !flags || !out) return set_error(SCPD_E_ARG, "scpd_create: null argument");
+    *out = nullptr;
+    const uint32_t n = cfg->n, par = cfg->par;
+    if (!is_pow2(n) || n < 2) return set_error(SCPD_E_CONFIG, "n must be a power of two >= 2");
+    if (n > (1u << 20)) return set_error(SCPD_E_UNSUPPORTED, "n above 2^20 not supported");
+    if (!is_pow2(par) || 2 * par > n)
+        return set_error(SCPD_E_CONFIG, "par must be a power of two with 2*par <= n (my_module.h:294)");
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (flags[i] > 1) return set_error(SCPD_E_CONFIG, "info flags must be 0 or 1");
+        k += flags[i];
+    }
+    if (k != cfg->k) return set_error(SCPD_E_CONFIG, "k differs from the number of information flags");
+    if (cfg->format != SCPD_FMT_CA2 && cfg->format != SCPD_FMT_SIGMAG)
+        return set_error(SCPD_E_CONFIG, "format must be SCPD_FMT_CA2 or SCPD_FMT_SIGMAG");
+    if (cfg->pruning > SCPD_PRUNE_R0_R1) return set_error(SCPD_E_CONFIG, "unknown pruning mode");
+    if (cfg->extended > 1) return set_error(SCPD_E_CONFIG, "extended must be 0 or 1");
+    if (cfg->llr_bits < 5 || cfg->llr_bits > 9)
+        return set_error(SCPD_E_CONFIG, "llr_bits outside 5..9 (range swept by script/script_tests.sh)");
+    if (cfg->format == SCPD_FMT_SIGMAG)
+        return set_error(SCPD_E_UNSUPPORTED, "SIGMAG arithmetic has no kernel in this build yet");
+    if (cfg->llr_bits < 6)
+        return set_error(SCPD_E_UNSUPPORTED,
+                         "llr_bits < 6: the +-31 quantiser alphabet wraps in the reference; no kernel for that yet");
+    const int log2par = ilog2(par);
+    // widest value inside the un-saturated leaf must fit int16 (Q + log2 PAR bits incl. the final sum)
+    if (cfg->extended && cfg->llr_bits + (uint32_t)log2par > 16)
+        return set_error(SCPD_E_UNSUPPORTED, "llr_bits + log2(par) > 16 does not fit the int16x2 datapath");
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    scpd_decoder* d = new (std::nothrow) scpd_decoder();
+    if (!d) return set_error(SCPD_E_NOMEM, "out of host memory");
+    d->cfg = *cfg;
+    d->device = device;
+    d->log2n = ilog2(n);
+    d->log2par = log2par;
+    d->wpf = n >= 32 ? n / 32 : 1;
+    d->sched_host = build_schedule(d->log2n, d->log2par, (int)cfg->extended, (int)cfg->pruning, flags, &d->stats);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete d;
+        return cuda_fail(e, "cudaGetDeviceProperties");
+    }
+    d->num_sms = prop.multiProcessorCount;
+    int rc = plan_layout(d);
+    if (rc != SCPD_OK) {
+        delete d;
+        return rc;
+    }
+    e = cudaMalloc(&d->d_sched, d->sched_host.size() * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(d->d_sched, d->sched_host.data(), d->sched_host.size() * sizeof(uint32_t),
+                       cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_counters, 6 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        scpd_destroy(d);
+        return cuda_fail(e, "schedule upload");
+    }
+    *out = d;
+    return SCPD_OK;
+}
+
+extern "C" void scpd_destroy(scpd_decoder* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaFree(d->d_sched);
+    cudaFree(d->d_ws);
+    cudaFree(d->d_llr);
+    cudaFree(d->d_xhat);
+    cudaFree(d->d_counters);
+    delete d;
+}
+
+extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, void* stream) {
+    if (!d) return set_error(SCPD_E_ARG, "scpd_decode: null decoder");
+    if (nframes == 0) return SCPD_OK;
+    if (!d_llr || !d_xhat) return set_error(SCPD_E_ARG, "scpd_decode: null buffer");
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gpw = 32 / d->group;
+    const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
+    const unsigned long long num_fp = (nframes + 1) / 2;
+    unsigned long long grid = (num_fp + fp_per_cta - 1) / fp_per_cta;
+    const unsigned long long max_grid = (unsigned long long)d->num_sms * d->ctas_per_sm;
+    if (grid > max_grid) grid = max_grid;
+    const size_t ws_need = (size_t)(grid * fp_per_cta * d->ws_words_per_fp * 4ull);
+    if (ws_need > d->ws_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_ws);
+        d->d_ws = nullptr;
+        d->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&d->d_ws, ws_need));
+        d->ws_bytes = ws_need;
+    }
+    DecodeParams p;
+    p.sched = d->d_sched;
+    p.llr = d_llr;
+    p.xhat = d_xhat;
+    p.nframes = nframes;
+    p.num_fp = num_fp;
+    p.n = d->cfg.n;
+    p.log2n = (uint32_t)d->log2n;
+    p.wpf = d->wpf;
+    p.satv = (1u << (d->cfg.llr_bits - 1)) - 1u;
+    p.log2par = (uint32_t)d->log2par;
+    p.extended = d->cfg.extended;
+    p.ls = d->ls;
+    p.beta_in_smem = d->beta_in_smem;
+    p.sm_words_per_fp = d->sm_words_per_fp;
+    p.ws = d->d_ws;
+    p.ws_words_per_fp = d->ws_words_per_fp;
+    const dim3 g((unsigned)grid), b((unsigned)(d->warps_per_cta * 32));
+    switch (d->group) {
+        case 8: sc_decode_generic_kernel<8><<<g, b, d->smem_bytes, st>>>(p); break;
+        case 16: sc_decode_generic_kernel<16><<<g, b, d->smem_bytes, st>>>(p); break;
+        default: sc_decode_generic_kernel<32><<<g, b, d->smem_bytes, st>>>(p); break;
+    }
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
+static int ensure_stage(scpd_decoder* d, size_t nframes) {
+    if (nframes <= d->stage_frames) return SCPD_OK;
+    cudaFree(d->d_llr);
+    cudaFree(d->d_xhat);
+    d->d_llr = nullptr;
+    d->d_xhat = nullptr;
+    d->stage_frames = 0;
+    CUDA_TRY(cudaMalloc(&d->d_llr, nframes * (size_t)d->cfg.n));
+    CUDA_TRY(cudaMalloc(&d->d_xhat, nframes * (size_t)d->wpf * 4));
+    d->stage_frames = nframes;
+    return SCPD_OK;
+}
+
+extern "C" int scpd_decode_host(scpd_decoder* d, const int8_t* h_llr, size_t nframes, uint32_t* h_xhat) {
+    if (!d) return set_error(SCPD_E_ARG, "scpd_decode_host: null decoder");
+    if (nframes == 0) return SCPD_OK;
+    if (!h_llr || !h_xhat) return set_error(SCPD_E_ARG, "scpd_decode_host: null buffer");
+    CUDA_TRY(cudaSetDevice(d->device));
+    int rc = ensure_stage(d, nframes);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d->d_llr, h_llr, nframes * (size_t)d->cfg.n, cudaMemcpyHostToDevice, 0));
+    rc = scpd_decode(d, d->d_llr, nframes, d->d_xhat, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_xhat, d->d_xhat, nframes * (size_t)d->wpf * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return SCPD_OK;
+}
+
+extern "C" int scpd_extract_info(scpd_decoder* d, const uint32_t* d_xhat, size_t nframes, uint32_t* d_uhat,
+                                 void* stream) {
+    if (!d) return set_error(SCPD_E_ARG, "scpd_extract_info: null decoder");
+    if (nframes == 0) return SCPD_OK;
+    if (!d_xhat || !d_uhat) return set_error(SCPD_E_ARG, "scpd_extract_info: null buffer");
+    CUDA_TRY(cudaSetDevice(d->device));
+    const unsigned grid = (unsigned)((nframes + 3) / 4);
+    polar_transform_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d->wpf, d->cfg.n, nframes, d_xhat, d_uhat);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
+extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
+    if (!d || !out) return set_error(SCPD_E_ARG, "scpd_get_config: null argument");
+    *out = d->cfg;
+    return SCPD_OK;
+}
+extern "C" int scpd_schedule_stats(const scpd_decoder* d, uint64_t* n_ops, uint64_t* n_fg) {
+    if (!d) return set_error(SCPD_E_ARG, "scpd_schedule_stats: null decoder");
+    if (n_ops) *n_ops = d->stats.n_ops;
+    if (n_fg) *n_fg = d->stats.n_f + d->stats.n_g;
+    return SCPD_OK;
+}
+extern "C" uint64_t scpd_launch_count(const scpd_decoder* d) { return d ? d->launches : 0; }
+
+extern "C" float scpd_sigma(float ebn0_db, float rate) {  // main.cpp:91-98
+    return 1.0f / sqrtf(2.f * rate * powf(10.f, ebn0_db / 10.f));
+}
+
+extern "C" int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nframes, uint8_t seed, float sigma,
+                                     const uint8_t* d_codeword, int per_frame, int8_t* d_llr, void* stream) {
+    if (nframes == 0) return SCPD_OK;
+    if (!d_llr) return set_error(SCPD_E_ARG, "scpd_channel_generate: null buffer");
+    if (!is_pow2(n) || n < 2) return set_error(SCPD_E_CONFIG, "n must be a power of two >= 2");
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    XsJumpTable jt;
+    int rc = jump_table_device(device, &jt);
+    if (rc) return rc;
+    const int log2c = n >= 64 ? ilog2(n / 64) : -1;
+    const unsigned grid = (unsigned)((nframes + 3) / 4);
+    channel_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, d_codeword, per_frame,
+                                                           d_llr, jt, log2c);
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
+extern "C" int scpd_count_errors(uint32_t n, size_t nframes, const uint32_t* d_xhat, const uint32_t* d_ref,
+                                 int per_frame, uint64_t* d_counters, void* stream) {
+    if (nframes == 0) return SCPD_OK;
+    if (!d_xhat || !d_counters) return set_error(SCPD_E_ARG, "scpd_count_errors: null buffer");
+    if (!is_pow2(n) || n < 2) return set_error(SCPD_E_CONFIG, "n must be a power of two >= 2");
+    const uint32_t wpf = n >= 32 ? n / 32 : 1;
+    unsigned long long blocks = (nframes + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    count_errors_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        wpf, n, nframes, d_xhat, d_ref, per_frame, (unsigned long long*)d_counters);
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
+extern "C" int scpd_run_ber(scpd_decoder* d, float ebn0_db, float rate, uint64_t first_frame, uint64_t nframes,
+                            uint8_t seed, const uint8_t* h_codeword, uint64_t h_counters[6]) {
+    if (!d || !h_counters) return set_error(SCPD_E_ARG, "scpd_run_ber: null argument");
+    CUDA_TRY(cudaSetDevice(d->device));
+    const uint32_t n = d->cfg.n;
+    // batch so that LLR staging stays around 1 GiB
+    size_t batch = (size_t)((1ull << 30) / n);
+    if (batch < 2) batch = 2;
+    if (batch > nframes) batch = (size_t)nframes;
+    if (batch == 0) {
+        std::memset(h_counters, 0, 6 * sizeof(uint64_t));
+        return SCPD_OK;
+    }
+    int rc = ensure_stage(d, batch);
+    if (rc) return rc;
+    uint8_t* d_cw = nullptr;
+    uint32_t* d_ref = nullptr;
+    if (h_codeword) {
+        std::vector<uint32_t> ref(d->wpf, 0);
+        for (uint32_t i = 0; i < n; i++)
+            if (h_codeword[i] & 1) ref[i >> 5] |= 1u << (i & 31);
+        CUDA_TRY(cudaMalloc(&d_cw, n));
+        CUDA_TRY(cudaMalloc(&d_ref, d->wpf * 4));
+        CUDA_TRY(cudaMemcpy(d_cw, h_codeword, n, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_ref, ref.data(), d->wpf * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemsetAsync(d->d_counters, 0, 6 * sizeof(unsigned long long), 0));
+    const float sigma = scpd_sigma(ebn0_db, rate);
+    for (uint64_t done = 0; done < nframes && rc == SCPD_OK; done += batch) {
+        const size_t nb = (size_t)((nframes - done < batch) ? nframes - done : batch);
+        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, d_cw, 0, d->d_llr, 0);
+        if (rc == SCPD_OK) rc = scpd_decode(d, d->d_llr, nb, d->d_xhat, 0);
+        if (rc == SCPD_OK) rc = scpd_count_errors(n, nb, d->d_xhat, d_ref, 0, (uint64_t*)d->d_counters, 0);
+        d->launches += 2;
+    }
+    cudaError_t e = cudaMemcpy(h_counters, d->d_counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_cw);
+    cudaFree(d_ref);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "counter readback");
+    return SCPD_OK;
+}
+
+extern "C" const char* scpd_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* scpd_status_string(int s) {
+    switch (s) {
+        case SCPD_OK: return "ok";
+        case SCPD_E_ARG: return "bad argument";
+        case SCPD_E_CONFIG: return "invalid configuration";
+        case SCPD_E_UNSUPPORTED: return "unsupported configuration";
+        case SCPD_E_IO: return "i/o error";
+        case SCPD_E_CUDA: return "cuda error";
+        case SCPD_E_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}

@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on identical
+quantised LLRs.  Bit-exact is the bar (integer/bit path)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+CONFIG_SETS = {
+    "c1": ("FB_N1024_K512", 1024, 512, 2.5),
+    "c2": ("frozen_n_4096_k_3072", 4096, 3072, 3.5),
+    "c3": ("frozen_n_32768_k_29492_snr_4_5", 32768, 29492, 4.5),
+    "c4": ("frozen_n_131072_k_117964", 131072, 117964, 4.5),
+    "c5": ("frozen_n_524288_k_262144", 524288, 262144, 2.0),
+}
+
+
+@pytest.fixture(scope="module")
+def scpd():
+    import torch
+    assert torch.cuda.is_available()
+    import sc_polar_decoder_hls_b200 as m
+    return m
+
+
+def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device"):
+    import torch
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags, par=par, llr_bits=q, fmt=scpd.FMT_CA2, extended=ext, pruning=prune)
+    if via == "host":
+        got = dec.decode_host(llr)
+    else:
+        x = dec.decode(torch.from_numpy(llr).cuda())
+        torch.cuda.synchronize()
+        got = x.cpu().numpy().view(np.uint32)
+    want = ol.decode_packed(n, par, q, 0, ext, flags, llr, threads=8)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} of {len(llr)} frames differ (first {bad[:5]}) {name} par={par} q={q} ext={ext} prune={prune}"
+    dec.close()
+
+
+def test_golden_codewords_noiseless(scpd):
+    """The reference's 9 stored codewords (sc_encoder.h:74-89) at sigma = 0 (LLR = +-4)."""
+    cws = ol.golden_codewords()
+    for key, name, n, k in (("cw8x4", "FB_N8_K4", 8, 4), ("cw512x256", "FB_N512_K256", 512, 256),
+                            ("cw1024x512", "FB_N1024_K512", 1024, 512)):
+        flags = scpd.packed_flags(name, n)
+        llr = np.where(cws[key] == 1, -4, 4).astype(np.int8)
+        for par in (2, 16):
+            if 2 * par > n:
+                continue
+            for prune in (0, 1, 2):
+                dec = scpd.Decoder(n, k, flags, par=par, pruning=prune)
+                got = ol.unpack_bits(dec.decode_host(llr), n)
+                assert (got == cws[key]).all(), (key, par, prune)
+
+
+@pytest.mark.parametrize("prune", [0, 1, 2])
+@pytest.mark.parametrize("par,q,ext", [(16, 8, 1), (16, 8, 0), (4, 8, 1), (64, 8, 1), (256, 8, 1), (16, 6, 1),
+                                       (16, 9, 1), (2, 7, 1), (1, 8, 1)])
+def test_c1_sweep(scpd, par, q, ext, prune):
+    name, n, k, snr = CONFIG_SETS["c1"]
+    rng = np.random.default_rng(par * 100 + q * 10 + ext)
+    llr = ol.test_llrs(rng, n, 600, k, snr)
+    _check(scpd, name, n, k, par, q, ext, prune, llr)
+
+
+def test_c1_headline_many_frames(scpd):
+    """>= 10^5 noisy frames of BASELINE config 1 at 2.5 dB (BASELINE.md parity gate), odd batch."""
+    name, n, k, snr = CONFIG_SETS["c1"]
+    import torch
+    flags = scpd.packed_flags(name, n)
+    nfr = 100001
+    cw = ol.golden_codewords()["cw1024x512"]
+    llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n), codeword=cw[1])
+    dec = scpd.Decoder(n, k, flags)
+    got = dec.decode(llr).cpu().numpy().view(np.uint32)
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr.cpu().numpy(), threads=8)
+    assert (got == want).all()
+    # and therefore identical error counts
+    ref = ol.pack_bits(cw[1][None, :])[0]
+    c_dev = scpd.count_errors(n, torch.from_numpy(got.view(np.int32)).cuda(), ref)
+    c_or = ol.count_errors(n, ol.unpack_bits(want, n), cw[1])
+    assert c_dev == c_or
+
+
+@pytest.mark.parametrize("key,nfr", [("c2", 300), ("c3", 24), ("c4", 6), ("c5", 3)])
+@pytest.mark.parametrize("prune", [0, 2])
+def test_baseline_configs(scpd, key, nfr, prune):
+    name, n, k, snr = CONFIG_SETS[key]
+    rng = np.random.default_rng(5)
+    llr = ol.test_llrs(rng, n, nfr, k, snr)
+    _check(scpd, name, n, k, 16, 8, 1, prune, llr)
+
+
+def test_zero_llr_fallback(scpd):
+    """All-zero and sparse LLR frames force the rate-1 plain-SC fallback on every node (G3/G10)."""
+    name, n, k, _ = CONFIG_SETS["c1"]
+    rng = np.random.default_rng(11)
+    llr = rng.integers(-31, 32, size=(64, n)).astype(np.int8)
+    llr[rng.random(llr.shape) < 0.6] = 0
+    llr[0] = 0
+    llr[1] = -1
+    llr[2] = 127
+    llr[3] = -127
+    for prune in (1, 2):
+        _check(scpd, name, n, k, 16, 8, 1, prune, llr)
+
+
+def test_ragged_and_empty_batches(scpd):
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags)
+    assert dec.decode_host(np.zeros((0, n), np.int8)).shape == (0, n // 32)
+    rng = np.random.default_rng(3)
+    for nfr in (1, 2, 3, 7, 8, 9, 31, 33, 257):
+        llr = ol.test_llrs(rng, n, nfr, k, snr)
+        got = dec.decode_host(llr)
+        want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+        assert (got == want).all(), nfr
+
+
+def test_host_path_equals_device_path(scpd):
+    name, n, k, snr = CONFIG_SETS["c2"]
+    rng = np.random.default_rng(4)
+    llr = ol.test_llrs(rng, n, 130, k, snr)
+    _check(scpd, name, n, k, 16, 8, 1, 2, llr, via="host")
+
+
+def test_arbitrary_flag_patterns(scpd):
+    """Frozen sets that are not polar-structured (any 0/1 table is a legal FB stream)."""
+    rng = np.random.default_rng(9)
+    import torch
+    for n in (4, 8, 32, 128, 512):
+        for trial in range(4):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-31, 32, size=(50, n)).astype(np.int8)
+            for par in (1, 2, 16):
+                if 2 * par > n:
+                    continue
+                for prune in (0, 1, 2):
+                    dec = scpd.Decoder(n, int(flags.sum()), flags, par=par, pruning=prune)
+                    got = dec.decode_host(llr)
+                    want = ol.decode_packed(n, par, 8, 0, 1, flags, llr)
+                    assert (got == want).all(), (n, trial, par, prune)
+
+
+def test_device_channel_matches_oracle_chain(scpd):
+    """Integer RNG stream is exact by construction; float libm differs in the last ulp, so LLRs
+    may differ by one quantisation step on a tiny fraction of samples (SURVEY 'Channel parity')."""
+    for n, nfr, first in ((1024, 64, 0), (1024, 5, 1000003), (64, 9, 17), (8, 40, 0), (4096, 6, 123456789)):
+        sig = scpd.sigma(2.5, 0.5)
+        cw = (np.arange(n) % 3 == 0).astype(np.uint8)
+        dev = scpd.channel_generate(n, nfr, sig, first_frame=first, codeword=cw).cpu().numpy()
+        ora = ol.channel(n, nfr, ol.sigma(2.5, 0.5), first_frame=first, codeword=cw)
+        diff = dev.astype(int) - ora.astype(int)
+        assert np.abs(diff).max() <= 1, (n, first)
+        assert (diff != 0).mean() < 2e-3, (n, first, (diff != 0).mean())
+
+
+def test_run_ber_counts(scpd):
+    """Whole device Monte-Carlo loop vs generate(device) -> oracle decode -> oracle count."""
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    cw = ol.golden_codewords()["cw1024x512"][0]
+    dec = scpd.Decoder(n, k, flags)
+    nfr = 4000
+    cnt = dec.run_ber(snr, k / n, nfr, first_frame=77, codeword=cw)
+    llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n), first_frame=77, codeword=cw).cpu().numpy()
+    want = ol.count_errors(n, ol.decode(n, 16, 8, 0, 1, flags, llr), cw)
+    assert cnt == want
+    assert cnt[3] == nfr and cnt[2] == nfr * n and 0 < cnt[1] < nfr // 10
+
+
+def test_extract_info_and_roundtrip_full_size(scpd):
+    """Size-independent property at BASELINE scale (c2, 2^17 frames = 512 MiB of LLRs): random
+    information words -> polar transform -> noiseless LLRs -> decode returns the codeword, and
+    u^ = x^ F^(x)n returns the information word (encode -> decode round trip)."""
+    import torch
+    name, n, k, _ = CONFIG_SETS["c2"]
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags)
+    nfr = 1 << 17
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = torch.randint(0, 2, (nfr, n), device="cuda", dtype=torch.int32, generator=g)
+    u *= torch.from_numpy(flags.astype(np.int32)).cuda()
+    # pack u, transform on the device with the product's own butterfly
+    w = torch.tensor([1 << i for i in range(31)] + [-(1 << 31)], device="cuda", dtype=torch.int64)
+    upk = (u.view(nfr, n // 32, 32).to(torch.int64) * w).sum(-1).to(torch.int32)
+    xpk = dec.extract_info(upk)  # F^(x)n is an involution: encode = same transform
+    shifts = torch.arange(32, device="cuda", dtype=torch.int32)
+    xbits = ((xpk.unsqueeze(-1) >> shifts) & 1).view(nfr, n)
+    llr = (4 - 8 * xbits).to(torch.int8)
+    del xbits, u
+    xhat = dec.decode(llr)
+    assert torch.equal(xhat, xpk)
+    assert torch.equal(dec.extract_info(xhat), upk)
+    # anchor the transform itself on the oracle for a few frames
+    some = ol.unpack_bits(upk[:4].cpu().numpy().view(np.uint32), n)
+    assert (ol.pack_bits(ol.polar_transform(some)) == xpk[:4].cpu().numpy().view(np.uint32)).all()
