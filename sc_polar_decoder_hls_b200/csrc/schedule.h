@@ -30,6 +30,7 @@ enum Op : uint32_t {
     OP_R1 = 7,     // all-information node: hard decision, plain-SC fallback if an LLR is 0
     OP_P2 = 8,     // two-bit terminal, Spec_P2 functions.h:367-384; leaf flags = (f0, f1)
     OP_P1 = 9,     // one-bit terminal, Spec_P1 functions.h:355-364; leaf flag bit0 = f
+    OP_SUB = 10,   // register subtree of size 2^l (fast kernel); followed by its node-type words
 };
 
 SCPD_HD static inline uint32_t op_make(uint32_t opc, uint32_t level, uint32_t offset, uint32_t nosat = 0,
@@ -52,6 +53,7 @@ struct ScheduleStats {
 
 struct ScheduleBuilder {
     int log2n, log2par, extended, pruning;
+    int log2sub = -1;  // >= 0: stop at nodes of this size and emit OP_SUB + descriptor (fast kernel)
     const uint8_t* flags;
     std::vector<uint32_t> psum;  // prefix sums of flags
     std::vector<uint32_t> ops;
@@ -61,6 +63,36 @@ struct ScheduleBuilder {
     // g of a node of size n is the un-saturated Function_G_ext iff the node lies inside the
     // PAR-wide leaf decoder and EXTENDED == 1 (Spec_P*_ext, functions.h:413-438 ...).
     uint32_t nosat(int l) const { return (extended && l <= log2par) ? 1u : 0u; }
+
+    // Node types of a register subtree, 2 bits per node in heap order (root 0, children 2i+1, 2i+2),
+    // sizes 2^l .. 2.  0 = mixed, 1 = all-frozen, 2 = all-information; for the size-2 nodes the code
+    // is the flag pair itself: 0 = (0,1), 1 = (0,0), 2 = (1,1), 3 = (1,0).
+    void emit_subtree(int l, uint32_t o) {
+        const uint32_t nodes = (1u << l) - 1u;
+        std::vector<uint32_t> words((2 * nodes + 31) / 32, 0u);
+        uint32_t heap = 0;
+        for (int d = 0; d < l; d++) {
+            const uint32_t sz = 1u << (l - d);
+            for (uint32_t k = 0; k < (1u << d); k++, heap++) {
+                const uint32_t c = count(o + k * sz, sz);
+                uint32_t t;
+                if (sz == 2) {
+                    const uint32_t f0 = flags[o + k * 2] & 1u, f1 = flags[o + k * 2 + 1] & 1u;
+                    t = (f0 == 0 && f1 == 1) ? 0u : (f0 == 0 && f1 == 0) ? 1u : (f0 == 1 && f1 == 1) ? 2u : 3u;
+                } else {
+                    t = (pruning >= 1 && c == 0) ? 1u : (pruning >= 2 && c == sz) ? 2u : 0u;
+                    if (c != 0 && c != sz) {
+                        // work estimate only (the kernel skips f when the left child is all-frozen)
+                        st.n_f += (count(o + k * sz, sz / 2) != 0 || pruning == 0) ? sz / 2 : 0;
+                        st.n_g += sz / 2;
+                    }
+                }
+                words[(2 * heap) >> 5] |= t << ((2 * heap) & 31);
+            }
+        }
+        ops.push_back(op_make(OP_SUB, l, o));
+        for (uint32_t w : words) ops.push_back(w);
+    }
 
     void emit(int l, uint32_t o) {
         const uint32_t n = 1u << l;
@@ -83,6 +115,10 @@ struct ScheduleBuilder {
             st.n_r1++;
             return;
         }
+        if (l == log2sub) {
+            emit_subtree(l, o);
+            return;
+        }
         const uint32_t h = n >> 1;
         const bool left_r0 = pruning >= 1 && count(o, h) == 0;
         const bool right_r0 = pruning >= 1 && count(o + h, h) == 0;
@@ -98,6 +134,7 @@ struct ScheduleBuilder {
         emit(l - 1, o);
         if (right_r0) {
             ops.push_back(op_make(OP_R0, l - 1, o + h));
+            ops.push_back(op_make(OP_H, l, o));  // left ^ 0; also moves the node between storage spaces
             st.n_r0++;
             return;
         }
@@ -110,8 +147,10 @@ struct ScheduleBuilder {
 
 // flags: n bytes, 1 = information bit.  Returns the op list terminated by OP_END.
 static inline std::vector<uint32_t> build_schedule(int log2n, int log2par, int extended, int pruning,
-                                                   const uint8_t* flags, ScheduleStats* stats) {
+                                                   const uint8_t* flags, ScheduleStats* stats,
+                                                   int log2sub = -1) {
     ScheduleBuilder b;
+    b.log2sub = log2sub;
     b.log2n = log2n;
     b.log2par = log2par;
     b.extended = extended;

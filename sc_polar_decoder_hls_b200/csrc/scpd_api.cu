@@ -2,6 +2,7 @@
 // Host logic only; the kernels are in decode_*.cuh / harness.cuh.  No CPU decode path exists.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "../../include/scpd.h"
+#include "decode_fast.cuh"
 #include "decode_generic.cuh"
 #include "harness.cuh"
 #include "internal.h"
@@ -109,6 +111,18 @@ struct scpd_decoder {
     int ctas_per_sm = 1, num_sms = 1;
     uint32_t* d_ws = nullptr;
     size_t ws_bytes = 0;
+    // fast-kernel plan (decode_fast.cuh); fast_group == 0: not available for this configuration
+    int fast_group = 0;
+    int fast_log2s = 0;
+    std::vector<uint32_t> fast_sched_host;
+    ScheduleStats fast_stats;
+    uint32_t* d_fast_sched = nullptr;
+    uint32_t fast_lsa = 0, fast_lsb = 0, fast_sm_alpha_cells = 0, fast_sm_stride = 0;
+    size_t fast_smem_bytes = 0;
+    unsigned long long fast_ws_stride = 0;
+    int fast_ctas_per_sm = 1;
+    uint8_t* d_fast_ws = nullptr;
+    size_t fast_ws_bytes = 0;
     // staging for scpd_decode_host / scpd_run_ber
     int8_t* d_llr = nullptr;
     uint32_t* d_xhat = nullptr;
@@ -123,6 +137,83 @@ static const void* generic_kernel_ptr(int group) {
         case 16: return (const void*)sc_decode_generic_kernel<16>;
         default: return (const void*)sc_decode_generic_kernel<32>;
     }
+}
+
+typedef void (*fast_kernel_t)(const FastParams);
+static fast_kernel_t fast_kernel_ptr(int group, int log2par, int ext) {
+    if (log2par == 4 && ext == 1) {
+        switch (group) {
+            case 2: return sc_decode_fast_kernel<2, 4, true>;
+            case 4: return sc_decode_fast_kernel<4, 4, true>;
+            case 8: return sc_decode_fast_kernel<8, 4, true>;
+            case 16: return sc_decode_fast_kernel<16, 4, true>;
+            default: return nullptr;
+        }
+    }
+    if (group == 8) {
+        if (log2par == 4 && ext == 0) return sc_decode_fast_kernel<8, 4, false>;
+        if (log2par == 2 && ext == 1) return sc_decode_fast_kernel<8, 2, true>;
+        if (log2par == 6 && ext == 1) return sc_decode_fast_kernel<8, 6, true>;
+    }
+    return nullptr;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// Decide whether the fast kernel applies and size its shared-memory / workspace layout.
+static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
+    d->fast_group = 0;
+    const char* ksel = std::getenv("SCPD_KERNEL");
+    if (ksel && std::strcmp(ksel, "generic") == 0) return SCPD_OK;
+    if (d->cfg.format != SCPD_FMT_CA2 || d->cfg.llr_bits > 8 || d->log2par < 1) return SCPD_OK;
+    int g = env_int("SCPD_GROUP", 8);
+    fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
+    if (!k) {
+        g = 8;
+        k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
+    }
+    if (!k) return SCPD_OK;
+    const int log2s = ilog2(8 * g);
+    if (d->log2par > log2s || d->log2n < log2s + 1) return SCPD_OK;  // leaf must sit inside the register subtree
+    d->fast_log2s = log2s;
+    d->fast_sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning, flags,
+                                        &d->fast_stats, log2s);
+    const int gpw = 32 / g;
+    const int fp_per_cta = d->warps_per_cta * gpw;
+    const size_t budget = (size_t)env_int("SCPD_SMEM_KB", 56) * 1024;
+    const size_t per_fp = budget / fp_per_cta;
+    const uint32_t n = d->cfg.n;
+    // alpha levels log2s..lsa (cell index (1 << l) + i  ->  2 << lsa cells), then the partial-sum block
+    int lsa = log2s;
+    for (int l = log2s; l <= d->log2n - 1; l++)
+        if ((size_t)(2u << l) * 2 <= per_fp * 6 / 10) lsa = l;
+    const size_t alpha_bytes = (size_t)(2u << lsa) * 2;
+    int lsb = log2s;
+    for (int l = log2s; l <= d->log2n; l++) {
+        const size_t cells = std::min<size_t>((size_t)2u << l, n);
+        if (alpha_bytes + cells * 2 <= per_fp) lsb = l;
+    }
+    const size_t beta_cells = std::min<size_t>((size_t)2u << lsb, n);
+    size_t stride = alpha_bytes + beta_cells * 2;
+    stride = (stride + 127) & ~(size_t)127;
+    if (g < 8) stride += 16 * g;  // spread the groups of a quarter-warp over distinct banks
+    d->fast_lsa = (uint32_t)lsa;
+    d->fast_lsb = (uint32_t)lsb;
+    d->fast_sm_alpha_cells = (uint32_t)(2u << lsa);
+    d->fast_sm_stride = (uint32_t)stride;
+    d->fast_smem_bytes = stride * fp_per_cta;
+    d->fast_ws_stride = ((unsigned long long)n * 6ull + 255ull) & ~255ull;
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->fast_smem_bytes));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, d->warps_per_cta * 32,
+                                                           d->fast_smem_bytes));
+    if (occ < 1) return SCPD_OK;  // does not fit: stay on the generic kernel
+    d->fast_ctas_per_sm = occ;
+    d->fast_group = g;
+    return SCPD_OK;
 }
 
 static int plan_layout(scpd_decoder* d) {
@@ -207,6 +298,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     }
     d->num_sms = prop.multiProcessorCount;
     int rc = plan_layout(d);
+    if (rc == SCPD_OK) rc = plan_fast(d, flags);
     if (rc != SCPD_OK) {
         delete d;
         return rc;
@@ -215,6 +307,12 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     if (e == cudaSuccess)
         e = cudaMemcpy(d->d_sched, d->sched_host.data(), d->sched_host.size() * sizeof(uint32_t),
                        cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && d->fast_group) {
+        e = cudaMalloc(&d->d_fast_sched, d->fast_sched_host.size() * sizeof(uint32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(d->d_fast_sched, d->fast_sched_host.data(), d->fast_sched_host.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&d->d_counters, 6 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         scpd_destroy(d);
@@ -229,10 +327,51 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaSetDevice(d->device);
     cudaFree(d->d_sched);
     cudaFree(d->d_ws);
+    cudaFree(d->d_fast_sched);
+    cudaFree(d->d_fast_ws);
     cudaFree(d->d_llr);
     cudaFree(d->d_xhat);
     cudaFree(d->d_counters);
     delete d;
+}
+
+static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
+    const int g = d->fast_group, gpw = 32 / g;
+    const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
+    const unsigned long long num_fp = (nframes + 1) / 2;
+    unsigned long long grid = (num_fp + fp_per_cta - 1) / fp_per_cta;
+    const unsigned long long max_grid = (unsigned long long)d->num_sms * d->fast_ctas_per_sm;
+    if (grid > max_grid) grid = max_grid;
+    const size_t ws_need = (size_t)(grid * fp_per_cta * d->fast_ws_stride);
+    if (ws_need > d->fast_ws_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_fast_ws);
+        d->d_fast_ws = nullptr;
+        d->fast_ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&d->d_fast_ws, ws_need));
+        d->fast_ws_bytes = ws_need;
+    }
+    FastParams p;
+    p.sched = d->d_fast_sched;
+    p.llr = d_llr;
+    p.xhat = d_xhat;
+    p.nframes = nframes;
+    p.num_fp = num_fp;
+    p.n = d->cfg.n;
+    p.log2n = (uint32_t)d->log2n;
+    p.wpf = d->wpf;
+    p.satv = (1u << (d->cfg.llr_bits - 1)) - 1u;
+    p.lsa = d->fast_lsa;
+    p.lsb = d->fast_lsb;
+    p.sm_alpha_cells = d->fast_sm_alpha_cells;
+    p.sm_stride = d->fast_sm_stride;
+    p.ws = d->d_fast_ws;
+    p.ws_stride = d->fast_ws_stride;
+    fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
+    k<<<dim3((unsigned)grid), dim3((unsigned)(d->warps_per_cta * 32)), d->fast_smem_bytes, st>>>(p);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
 }
 
 extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, void* stream) {
@@ -241,6 +380,7 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     if (!d_llr || !d_xhat) return set_error(SCPD_E_ARG, "scpd_decode: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->fast_group && (reinterpret_cast<uintptr_t>(d_llr) & 7u) == 0) return decode_fast(d, d_llr, nframes, d_xhat, st);
     const int gpw = 32 / d->group;
     const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
     const unsigned long long num_fp = (nframes + 1) / 2;
@@ -332,8 +472,9 @@ extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
 }
 extern "C" int scpd_schedule_stats(const scpd_decoder* d, uint64_t* n_ops, uint64_t* n_fg) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_schedule_stats: null decoder");
-    if (n_ops) *n_ops = d->stats.n_ops;
-    if (n_fg) *n_fg = d->stats.n_f + d->stats.n_g;
+    const ScheduleStats& st = d->fast_group ? d->fast_stats : d->stats;
+    if (n_ops) *n_ops = st.n_ops;
+    if (n_fg) *n_fg = st.n_f + st.n_g;
     return SCPD_OK;
 }
 extern "C" uint64_t scpd_launch_count(const scpd_decoder* d) { return d ? d->launches : 0; }

@@ -1,0 +1,185 @@
+// warp_emu.cpp -- TEST INFRASTRUCTURE.  Runs the product's fast decode kernel source
+// (csrc/decode_fast.cuh, compiled as C++ through tests/emu/fake_cuda/cuda_runtime.h) on the CPU:
+// one ucontext fiber per lane, warp collectives resolved when all 32 lanes have arrived.
+// Used to debug kernel logic and to cover it in the CPU-only test tier.  Never a decode path.
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cuda_runtime.h"
+// keep this include after the fake runtime
+#include "../../sc_polar_decoder_hls_b200/csrc/decode_fast.cuh"
+
+namespace scpd {
+__attribute__((aligned(16))) uint8_t smem_fast[232448];
+}
+
+namespace cuda_emu {
+thread_local LaneCtx* cur = nullptr;
+namespace {
+constexpr int W = 32;
+struct Warp {
+    ucontext_t main_ctx;
+    ucontext_t ctx[W];
+    std::vector<char> stacks[W];
+    LaneCtx lanes[W];
+    bool done[W];
+    int running = 0;
+    uint32_t exch[2][W];
+    unsigned long long arrivals[2] = {0, 0};
+    unsigned long long phase[W];
+    void (*body)(void*) = nullptr;
+    void* arg = nullptr;
+};
+Warp* g_warp = nullptr;
+void yield_lane() {
+    Warp* w = g_warp;
+    const int me = w->running;
+    swapcontext(&w->ctx[me], &w->main_ctx);
+}
+int arrive(uint32_t v) {  // returns buffer index; blocks until all lanes have arrived
+    Warp* w = g_warp;
+    const int me = w->running;
+    const unsigned long long ph = w->phase[me]++;
+    const int buf = (int)(ph & 1);
+    w->exch[buf][me] = v;
+    w->arrivals[buf]++;
+    while (w->arrivals[buf] < (unsigned long long)W * (ph / 2 + 1)) yield_lane();
+    return buf;
+}
+void trampoline() {
+    Warp* w = g_warp;
+    const int me = w->running;
+    cur = &w->lanes[me];
+    w->body(w->arg);
+    w->done[me] = true;
+    swapcontext(&w->ctx[me], &w->main_ctx);
+}
+}  // namespace
+uint32_t collective_exchange(uint32_t v, int src_lane) {
+    const int buf = arrive(v);
+    return g_warp->exch[buf][src_lane & 31];
+}
+uint32_t collective_ballot(bool pred) {
+    const int buf = arrive(pred ? 1u : 0u);
+    uint32_t r = 0;
+    for (int i = 0; i < W; i++) r |= (g_warp->exch[buf][i] & 1u) << i;
+    return r;
+}
+void collective_sync() { (void)arrive(0); }
+
+// run one warp (32 lanes) of `body` to completion
+void run_warp(void (*body)(void*), void* arg, dim3 block, dim3 grid, dim3 bdim, int warp_index) {
+    Warp* w = new Warp();
+    g_warp = w;
+    w->body = body;
+    w->arg = arg;
+    for (int i = 0; i < W; i++) {
+        w->stacks[i].resize(1 << 18);
+        w->done[i] = false;
+        w->phase[i] = 0;
+        w->lanes[i].tid.x = warp_index * 32 + i;
+        w->lanes[i].bid = block;
+        w->lanes[i].gdim = grid;
+        w->lanes[i].bdim = bdim;
+        w->lanes[i].lane = i;
+        getcontext(&w->ctx[i]);
+        w->ctx[i].uc_stack.ss_sp = w->stacks[i].data();
+        w->ctx[i].uc_stack.ss_size = w->stacks[i].size();
+        w->ctx[i].uc_link = &w->main_ctx;
+        makecontext(&w->ctx[i], (void (*)())trampoline, 0);
+    }
+    for (;;) {
+        bool all = true;
+        for (int i = 0; i < W; i++) {
+            if (w->done[i]) continue;
+            all = false;
+            w->running = i;
+            cur = &w->lanes[i];
+            swapcontext(&w->main_ctx, &w->ctx[i]);
+        }
+        if (all) break;
+    }
+    delete w;
+    g_warp = nullptr;
+}
+}  // namespace cuda_emu
+
+using namespace scpd;
+
+namespace {
+struct Launch {
+    FastParams p;
+    int g, log2par, ext;
+};
+template <int G, int LP, bool EXT>
+void body_t(void* a) {
+    sc_decode_fast_kernel<G, LP, EXT>(static_cast<Launch*>(a)->p);
+}
+void (*pick(int g, int lp, int ext))(void*) {
+#define CASE(G, LP, E) \
+    if (g == G && lp == LP && ext == (E ? 1 : 0)) return body_t<G, LP, E>;
+    CASE(1, 4, true) CASE(2, 4, true) CASE(4, 4, true) CASE(8, 4, true) CASE(16, 4, true) CASE(32, 4, true)
+    CASE(8, 4, false) CASE(8, 2, true) CASE(8, 6, true) CASE(4, 2, true) CASE(2, 1, true) CASE(4, 4, false)
+#undef CASE
+    return nullptr;
+}
+}  // namespace
+
+extern "C" {
+// Emulates the fast kernel with `warps` warps per CTA and `grid` CTAs.  lsa/lsb as in FastParams
+// (pass -1 for "everything in shared memory").  Returns 0, or -1 if the variant is not compiled in.
+int emu_fast_decode(int g, int log2n, int log2par, int llr_bits, int extended, int pruning, const uint8_t* flags,
+                    const int8_t* llr, size_t nframes, uint32_t* xhat, int lsa, int lsb, int warps, int grid) {
+    void (*body)(void*) = pick(g, log2par, extended);
+    if (!body) return -1;
+    const int log2s = 3;
+    int ls = log2s;
+    for (int x = g; x > 1; x >>= 1) ls++;
+    if (log2par > ls || log2n < ls + 1) return -2;
+    ScheduleStats st;
+    std::vector<uint32_t> sched = build_schedule(log2n, log2par, extended, pruning, flags, &st, ls);
+    const uint32_t n = 1u << log2n;
+    Launch L;
+    L.g = g;
+    FastParams& p = L.p;
+    p.sched = sched.data();
+    p.llr = llr;
+    p.xhat = xhat;
+    p.nframes = nframes;
+    p.num_fp = (nframes + 1) / 2;
+    p.n = n;
+    p.log2n = (uint32_t)log2n;
+    p.wpf = n / 32;
+    p.satv = (1u << (llr_bits - 1)) - 1u;
+    if (lsa < 0) lsa = log2n - 1;
+    if (lsb < 0) lsb = log2n;
+    if (lsa < ls) lsa = ls;
+    if (lsb < ls) lsb = ls;
+    p.lsa = (uint32_t)lsa;
+    p.lsb = (uint32_t)lsb;
+    p.sm_alpha_cells = 2u << lsa;
+    const size_t beta_cells = std::min<size_t>((size_t)2u << lsb, n);
+    size_t stride = ((size_t)p.sm_alpha_cells * 2 + beta_cells * 2 + 127) & ~(size_t)127;
+    if (g < 8) stride += 16 * g;
+    p.sm_stride = (uint32_t)stride;
+    const int gpw = 32 / g;
+    const size_t fp_per_cta = (size_t)warps * gpw;
+    if (stride * fp_per_cta > sizeof(smem_fast)) return -3;
+    p.ws_stride = ((unsigned long long)n * 6ull + 255ull) & ~255ull;
+    std::vector<uint8_t> ws((size_t)grid * fp_per_cta * p.ws_stride + 256, 0xCD);
+    p.ws = reinterpret_cast<uint8_t*>(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
+    dim3 gd, bd;
+    gd.x = (unsigned)grid;
+    bd.x = (unsigned)warps * 32;
+    for (int b = 0; b < grid; b++) {
+        std::memset(smem_fast, 0xEE, sizeof(smem_fast));
+        dim3 bi;
+        bi.x = (unsigned)b;
+        for (int w = 0; w < warps; w++) cuda_emu::run_warp(body, &L, bi, gd, bd, w);
+    }
+    return 0;
+}
+}

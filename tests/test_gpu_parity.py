@@ -40,6 +40,30 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device"):
     dec.close()
 
 
+@pytest.fixture(params=["auto", "generic", "fast2", "fast4", "fast16"])
+def kernel_mode(request, monkeypatch):
+    """Selects the decode kernel through the library's environment switches (read in scpd_create)."""
+    mode = request.param
+    monkeypatch.delenv("SCPD_KERNEL", raising=False)
+    monkeypatch.delenv("SCPD_GROUP", raising=False)
+    if mode == "generic":
+        monkeypatch.setenv("SCPD_KERNEL", "generic")
+    elif mode.startswith("fast"):
+        monkeypatch.setenv("SCPD_GROUP", mode[4:])
+    return mode
+
+
+@pytest.mark.parametrize("key,nfr", [("c1", 1500), ("c2", 300), ("c3", 16)])
+@pytest.mark.parametrize("prune", [0, 1, 2])
+def test_every_kernel_variant(scpd, kernel_mode, key, nfr, prune):
+    name, n, k, snr = CONFIG_SETS[key]
+    rng = np.random.default_rng(21)
+    llr = ol.test_llrs(rng, n, nfr, k, snr)
+    llr[-1] = 0
+    llr[-2][::7] = 0
+    _check(scpd, name, n, k, 16, 8, 1, prune, llr)
+
+
 def test_golden_codewords_noiseless(scpd):
     """The reference's 9 stored codewords (sc_encoder.h:74-89) at sigma = 0 (LLR = +-4)."""
     cws = ol.golden_codewords()
