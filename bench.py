@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the SC polar decode path (BASELINE.json metric).
+
+Workload (N=1 and every N): BASELINE.json configs[1] -- N=4096, K=3072
+(Generated_Frozen_Bit/frozen_n_4096_k_3072), 2^20 frames per GPU per step, plain-SC results
+(CA2, LLR_BITS=8, PAR=16, EXTENDED=1; all-frozen / all-information subtrees skipped where that is
+bit-identical), all-zero codeword through the device BPSK/AWGN/quantiser chain at Eb/N0 = 3.5 dB.
+A "step" is one scpd_decode() over the resident 4 GiB LLR batch (far larger than the 126 MB L2).
+
+  value  : information-bit Gb/s with the LLRs already in HBM (device-timed, CUDA events)
+  e2e    : the same through scpd_decode_host(): pinned host LLRs -> H2D -> decode -> D2H, every step
+  N > 1  : frames are sharded across ranks (one process per GPU, torchrun); no data-path collective,
+           only a barrier and a max-reduction of the elapsed time ("weak" scaling).
+
+`--impl reference` times the reference's own CPU decoder (oracle/_ref, i.e. src/module/my_module.h
+compiled natively; the oracle port if that library is absent) on the host cores for the same
+workload, on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = dict(name="frozen_n_4096_k_3072", n=4096, k=3072, ebn0=3.5, frames=1 << 20, par=16, llr_bits=8)
+METRIC = "info-bit Gb/s decoded (bit-exact)"
+UNIT = "Gb/s"
+
+
+# ----------------------------------------------------------------------------- sharding helpers
+def shard_range(total, rank, world):
+    """Frames [lo, hi) of a stream of `total` frames owned by `rank` (contiguous, balanced)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sum_counters(t):
+    """Sum the six error counters over ranks (the only exchange of the path)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def max_over_ranks(x, device="cpu"):
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return float(x)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def _ref_worker(args):
+    so, flags, llr = args
+    R = ctypes.CDLL(so)
+    out = np.zeros(llr.shape, np.uint8)
+    rc = R.ref_decode(flags.ctypes.data_as(ctypes.c_void_p), llr.ctypes.data_as(ctypes.c_void_p),
+                      ctypes.c_size_t(llr.shape[0]), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return int(out.sum())
+
+
+def cpu_decode_rate(flags, llr, kind, cores):
+    """Decode `llr` on the host cores; returns (seconds, kind actually used)."""
+    import oracle_lib as ol
+    so = os.path.join(ROOT, "oracle", "_ref", "refdec_n4096_p16_q8_ca2_e1.so")
+    if kind == "reference" and os.path.exists(so):
+        import multiprocessing as mp
+        parts = [p for p in np.array_split(llr, cores) if len(p)]
+        with mp.get_context("fork").Pool(len(parts)) as pool:
+            pool.map(_ref_worker, [(so, flags, p[:1]) for p in parts])  # load the library, touch memory
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(so, flags, p) for p in parts])
+            return time.perf_counter() - t0, "reference"
+    ol.decode_packed(CFG["n"], CFG["par"], CFG["llr_bits"], 0, 1, flags, llr[:cores], threads=cores)
+    t0 = time.perf_counter()
+    ol.decode_packed(CFG["n"], CFG["par"], CFG["llr_bits"], 0, 1, flags, llr, threads=cores)
+    return time.perf_counter() - t0, "port"
+
+
+def host_sample(nframes):
+    """Same workload as the GPU arm, produced by the oracle's channel chain (identical statistics)."""
+    import oracle_lib as ol
+    return ol.channel(CFG["n"], nframes, ol.sigma(CFG["ebn0"], CFG["k"] / CFG["n"]))
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import sc_polar_decoder_hls_b200 as scpd
+    flags = scpd.packed_flags(CFG["name"], CFG["n"])
+    cores = os.cpu_count() or 1
+    # probe the rate, then size the per-step sample so the whole run stays within a few minutes
+    probe = host_sample(4 * cores)
+    sec, kind = cpu_decode_rate(flags, probe, "reference", cores)
+    per_frame = sec / len(probe)
+    budget = 150.0 / max(1, a.steps + a.warmup)
+    nfr = int(max(cores, min(1 << 16, budget / per_frame)))
+    llr = host_sample(nfr)
+    for _ in range(a.warmup):
+        cpu_decode_rate(flags, llr, kind, cores)
+    total = 0.0
+    for _ in range(a.steps):
+        total += cpu_decode_rate(flags, llr, kind, cores)[0]
+    ms = 1e3 * total / a.steps
+    val = nfr * CFG["k"] / (ms * 1e-3) / 1e9
+    sample = f"{nfr} frames N={CFG['n']} K={CFG['k']} per step, decode only, {cores} host processes"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: N=4096 K=3072 plain SC, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB",
+                       "frames_per_step": nfr, "flush": "n/a (host)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    import sc_polar_decoder_hls_b200 as scpd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, k = CFG["n"], CFG["k"]
+    frames = a.frames
+    flags = scpd.packed_flags(CFG["name"], n)
+    dec = scpd.Decoder(n, k, flags, par=CFG["par"], llr_bits=CFG["llr_bits"], fmt=scpd.FMT_CA2, extended=1,
+                       pruning=scpd.PRUNE_R0_R1, device=local)
+    # this rank's shard of the global frame stream (weak scaling: `frames` per rank)
+    lo, hi = shard_range(frames * world, rank, world)
+    llr = scpd.channel_generate(n, hi - lo, scpd.sigma(CFG["ebn0"], k / n), first_frame=lo, device=local)
+    xhat = torch.empty((hi - lo, n // 32), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    # ---- parity spot check against the oracle on this very batch (not timed)
+    import oracle_lib as ol
+    dec.decode(llr, xhat)
+    torch.cuda.synchronize()
+    chk = min(256, hi - lo)
+    want = ol.decode_packed(n, CFG["par"], CFG["llr_bits"], 0, 1, flags, llr[:chk].cpu().numpy(), threads=8)
+    assert (xhat[:chk].cpu().numpy().view(np.uint32) == want).all(), "CUDA decode differs from the oracle"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(a.warmup):
+        dec.decode(llr, xhat)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = dec.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        dec.decode(llr, xhat)
+    e1.record()
+    barrier()
+    launches = dec.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_step = ms_total / a.steps
+    value = world * (hi - lo) * k / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer entry point (pinned memory, copies inside the timed region)
+    h_llr = torch.empty((hi - lo, n), dtype=torch.int8, pin_memory=True)
+    h_llr.copy_(llr)
+    h_out = torch.empty((hi - lo, n // 32), dtype=torch.int32, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        scpd.check(scpd.lib.scpd_decode_host(dec._h, h_llr.data_ptr(), hi - lo, h_out.data_ptr()))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
+    e2e_val = world * (hi - lo) * k / (e2e_ms * 1e-3) / 1e9
+    assert (h_out[:chk].numpy().view(np.uint32) == want).all()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = (hi - lo) * (n + n // 8)  # int8 LLR in + packed x^ out per frame
+        ach = alg_bytes / (ms_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        cores = os.cpu_count() or 1
+        nfr_cpu = 64 * cores
+        sec, kind = cpu_decode_rate(flags, llr[:nfr_cpu].cpu().numpy(), "port", cores)
+        cpu_val = nfr_cpu * k / sec / 1e9
+        ops, fg = dec.schedule_stats()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: N=4096 K=3072 plain SC, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB",
+                       "frames_per_step_per_gpu": hi - lo, "frames_per_s": world * (hi - lo) / (ms_step * 1e-3),
+                       "coded_gbps": value * n / k, "schedule_ops": ops, "fg_updates_per_frame": fg,
+                       "flush": "inputs (4 GiB of LLRs per GPU) larger than the 126 MB L2",
+                       "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "note": "decode is integer-ALU bound: see DESIGN.md for the instruction roofline"},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{nfr_cpu} frames of the same batch, decode only, {cores} threads"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((hi - lo) * n),
+                    "d2h_bytes_per_step": int((hi - lo) * (n // 32) * 4), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=CFG["frames"], help="frames per GPU per step")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    import __graft_entry__ as ge
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        ge.build()
+    else:  # other local ranks wait for rank 0's build instead of racing nvcc
+        from sc_polar_decoder_hls_b200.build import wait_for_lib
+        wait_for_lib()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,5 +37,17 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+def wait_for_lib(timeout=600.0):
+    """Block until another process has finished building an up-to-date libscpd.so."""
+    import time
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+            time.sleep(0.5)
+            return LIB
+        time.sleep(0.5)
+    raise RuntimeError("timed out waiting for libscpd.so")
+
+
 if __name__ == "__main__":
     print(build_lib(force=True, verbose=True))

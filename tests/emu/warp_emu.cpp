@@ -121,7 +121,7 @@ void body_t(void* a) {
 void (*pick(int g, int lp, int ext))(void*) {
 #define CASE(G, LP, E) \
     if (g == G && lp == LP && ext == (E ? 1 : 0)) return body_t<G, LP, E>;
-    CASE(1, 4, true) CASE(2, 4, true) CASE(4, 4, true) CASE(8, 4, true) CASE(16, 4, true) CASE(32, 4, true)
+    CASE(1, 3, true) CASE(2, 4, true) CASE(4, 4, true) CASE(8, 4, true) CASE(16, 4, true) CASE(32, 4, true)
     CASE(8, 4, false) CASE(8, 2, true) CASE(8, 6, true) CASE(4, 2, true) CASE(2, 1, true) CASE(4, 4, false)
 #undef CASE
     return nullptr;

@@ -24,6 +24,29 @@ def scpd():
     return m
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle(n, par, q, ext, flags, llr):
+    """Oracle output is independent of pruning mode and kernel variant: compute once per input."""
+    key = (n, par, q, ext, flags.tobytes(), llr.shape, hash(llr.tobytes()))
+    if key not in _ORACLE_CACHE:
+        if len(_ORACLE_CACHE) > 64:
+            _ORACLE_CACHE.clear()
+        _ORACLE_CACHE[key] = ol.decode_packed(n, par, q, 0, ext, flags, llr, threads=8)
+    return _ORACLE_CACHE[key]
+
+
+_LLR_CACHE = {}
+
+
+def _llrs(seed, n, nfr, k, snr):
+    key = (seed, n, nfr, k, snr)
+    if key not in _LLR_CACHE:
+        _LLR_CACHE[key] = ol.test_llrs(np.random.default_rng(seed), n, nfr, k, snr)
+    return _LLR_CACHE[key]
+
+
 def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device"):
     import torch
     flags = scpd.packed_flags(name, n)
@@ -34,7 +57,7 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device"):
         x = dec.decode(torch.from_numpy(llr).cuda())
         torch.cuda.synchronize()
         got = x.cpu().numpy().view(np.uint32)
-    want = ol.decode_packed(n, par, q, 0, ext, flags, llr, threads=8)
+    want = _oracle(n, par, q, ext, flags, llr)
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, f"{bad.size} of {len(llr)} frames differ (first {bad[:5]}) {name} par={par} q={q} ext={ext} prune={prune}"
     dec.close()
@@ -53,12 +76,11 @@ def kernel_mode(request, monkeypatch):
     return mode
 
 
-@pytest.mark.parametrize("key,nfr", [("c1", 1500), ("c2", 300), ("c3", 16)])
+@pytest.mark.parametrize("key,nfr", [("c1", 600), ("c2", 150), ("c3", 8)])
 @pytest.mark.parametrize("prune", [0, 1, 2])
 def test_every_kernel_variant(scpd, kernel_mode, key, nfr, prune):
     name, n, k, snr = CONFIG_SETS[key]
-    rng = np.random.default_rng(21)
-    llr = ol.test_llrs(rng, n, nfr, k, snr)
+    llr = _llrs(21, n, nfr, k, snr).copy()
     llr[-1] = 0
     llr[-2][::7] = 0
     _check(scpd, name, n, k, 16, 8, 1, prune, llr)
@@ -85,8 +107,7 @@ def test_golden_codewords_noiseless(scpd):
                                        (16, 9, 1), (2, 7, 1), (1, 8, 1)])
 def test_c1_sweep(scpd, par, q, ext, prune):
     name, n, k, snr = CONFIG_SETS["c1"]
-    rng = np.random.default_rng(par * 100 + q * 10 + ext)
-    llr = ol.test_llrs(rng, n, 600, k, snr)
+    llr = _llrs(par * 100 + q * 10 + ext, n, 400, k, snr)
     _check(scpd, name, n, k, par, q, ext, prune, llr)
 
 
@@ -113,8 +134,7 @@ def test_c1_headline_many_frames(scpd):
 @pytest.mark.parametrize("prune", [0, 2])
 def test_baseline_configs(scpd, key, nfr, prune):
     name, n, k, snr = CONFIG_SETS[key]
-    rng = np.random.default_rng(5)
-    llr = ol.test_llrs(rng, n, nfr, k, snr)
+    llr = _llrs(5, n, nfr, k, snr)
     _check(scpd, name, n, k, 16, 8, 1, prune, llr)
 
 

@@ -1,0 +1,150 @@
+"""CPU tier: host logic of the product (schedule compiler, pruning rules, kernel source under the
+warp emulator) against the oracle, and the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sc_polar_decoder_hls_b200 as scpd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIBS = {}
+
+
+def _emu_lib(name):
+    """Loaded lazily: the session fixture (conftest.py) rebuilds stale emulator libraries first."""
+    if name not in _LIBS:
+        _LIBS[name] = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", name))
+        if name == "libschedule_emu.so":
+            _LIBS[name].emu_decode.restype = ctypes.c_longlong
+    return _LIBS[name]
+
+
+def _emu(flags, n, par, q, ext, prune, llr, force=0):
+    out = np.zeros(llr.shape, np.uint8)
+    nops, nfg = ctypes.c_uint64(), ctypes.c_uint64()
+    fb = _emu_lib('libschedule_emu.so').emu_decode(int(np.log2(n)), int(np.log2(par)), q, ext, prune, ol.P(flags), ol.P(llr),
+                        ctypes.c_size_t(len(llr)), ol.P(out), force, ctypes.byref(nops), ctypes.byref(nfg))
+    assert fb >= 0
+    return out, fb, nops.value, nfg.value
+
+
+@pytest.mark.parametrize("name,n,k", [("FB_N8_K4", 8, 4), ("FB_N512_K256", 512, 256),
+                                      ("FB_N1024_K512", 1024, 512), ("frozen_n_4096_k_3072", 4096, 3072)])
+def test_schedule_interpreter_equals_oracle(name, n, k):
+    """Every pruning mode of the schedule (and the forced rate-1 fallback walk) is bit-identical to
+    plain SC, for PAR 1..256, Q 6/8/9, EXTENDED 0/1."""
+    flags = scpd.packed_flags(name, n)
+    rng = np.random.default_rng(7)
+    for par in (1, 2, 4, 16, 64, 256):
+        if 2 * par > n:
+            continue
+        for q, ext in ((8, 1), (8, 0), (6, 1), (9, 1)):
+            if ext and q + int(np.log2(par)) > 16:
+                continue
+            nfr = 12 if n >= 1024 else 40
+            llr = ol.test_llrs(rng, n, nfr, k, maxabs=min(31, (1 << (q - 1)) - 1))
+            llr[-1][rng.random(n) < 0.5] = 0
+            want = ol.decode(n, par, q, 0, ext, flags, llr)
+            for prune, force in ((0, 0), (1, 0), (2, 0), (2, 1)):
+                got, fb, nops, nfg = _emu(flags, n, par, q, ext, prune, llr, force)
+                assert (got == want).all(), (par, q, ext, prune, force)
+
+
+def test_schedule_pruning_reduces_work():
+    n, k = 1024, 512
+    flags = scpd.packed_flags("FB_N1024_K512", n)
+    llr = np.zeros((1, n), np.int8)
+    work = [_emu(flags, n, 16, 8, 1, p, llr)[3] for p in (0, 1, 2)]
+    assert work[0] == n * 10 - n  # every f and g above the 2-bit terminals: N log2 N - N
+    assert work[0] > work[1] > work[2]
+
+
+def test_arbitrary_flag_tables():
+    rng = np.random.default_rng(2)
+    for n in (4, 8, 16, 64, 256):
+        for _ in range(20):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-31, 32, size=(30, n)).astype(np.int8)
+            for par in (1, 2, 4, 16):
+                if 2 * par > n:
+                    continue
+                want = ol.decode(n, par, 8, 0, 1, flags, llr)
+                for prune in (0, 1, 2):
+                    assert (_emu(flags, n, par, 8, 1, prune, llr)[0] == want).all()
+
+
+def _wemu(g, flags, n, par, ext, prune, llr, lsa=-1, lsb=-1, warps=1, grid=1):
+    out = np.zeros((len(llr), n // 32), np.uint32)
+    rc = _emu_lib('libwarp_emu.so').emu_fast_decode(g, int(np.log2(n)), int(np.log2(par)), 8, ext, prune, ol.P(flags), ol.P(llr),
+                              ctypes.c_size_t(len(llr)), ol.P(out), lsa, lsb, warps, grid)
+    assert rc == 0, rc
+    return out
+
+
+@pytest.mark.parametrize("g,par,ext", [(1, 8, 1), (2, 16, 1), (4, 16, 1), (8, 16, 1), (16, 16, 1), (32, 16, 1),
+                                       (8, 16, 0), (8, 4, 1), (8, 64, 1), (4, 4, 1), (2, 2, 1)])
+def test_fast_kernel_source_under_warp_emulator(g, par, ext):
+    """decode_fast.cuh executed lane by lane on the CPU (tests/emu/warp_emu.cpp): cell packing,
+    register subtree, node-type descriptors, shared/workspace storage split, ragged batches."""
+    n, k = 1024, 512
+    flags = scpd.packed_flags("FB_N1024_K512", n)
+    rng = np.random.default_rng(g * 10 + par)
+    nfr = 2 * (32 // g) + 3  # more than one warp pass, odd tail
+    llr = ol.test_llrs(rng, n, nfr, k)
+    llr[0] = 0
+    llr[1][::5] = 0
+    want = ol.decode_packed(n, par, 8, 0, ext, flags, llr)
+    for prune in (0, 1, 2):
+        assert (_wemu(g, flags, n, par, ext, prune, llr) == want).all(), prune
+    ls = 3 + int(np.log2(g))
+    if ls + 2 <= 9:
+        assert (_wemu(g, flags, n, par, ext, 2, llr, lsa=ls + 1, lsb=ls, warps=2, grid=2) == want).all()
+
+
+def test_fast_kernel_emulated_on_other_codes():
+    rng = np.random.default_rng(4)
+    for name, n, k in (("frozen_n_4096_k_3072", 4096, 3072), ("FB_N512_K256", 512, 256), ("FB_N2048_K1024", 2048, 1024)):
+        flags = scpd.packed_flags(name, n)
+        llr = ol.test_llrs(rng, n, 9, k, 3.0)
+        want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+        for g in (4, 8):
+            assert (_wemu(g, flags, n, 16, 1, 2, llr, lsa=8, lsb=7) == want).all(), (name, g)
+    for n in (128, 256):  # random flag tables
+        for _ in range(6):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-31, 32, size=(10, n)).astype(np.int8)
+            want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+            for prune in (0, 2):
+                assert (_wemu(8, flags, n, 16, 1, prune, llr) == want).all()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "scpd.h")).read()
+    declared = set(re.findall(r"\b(scpd_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"scpd_config", "scpd_decoder", "scpd_status", "scpd_format", "scpd_pruning"}
+    assert declared == set(scpd.EXPORTS), declared ^ set(scpd.EXPORTS)
+    raw = ctypes.CDLL(scpd.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Configuration errors are reported before any CUDA call, with the reference's constraints."""
+    flags = scpd.packed_flags("FB_N1024_K512", 1024)
+    bad = [dict(n=1000), dict(par=1024), dict(par=3), dict(k=511), dict(llr_bits=4), dict(llr_bits=12),
+           dict(fmt=7), dict(pruning=9), dict(extended=2)]
+    for kw in bad:
+        args = dict(n=1024, k=512, par=16, llr_bits=8, fmt=0, extended=1, pruning=2)
+        args.update(kw)
+        fl = flags if args["n"] == 1024 else np.zeros(args["n"], np.uint8)
+        with pytest.raises(scpd.ScpdError) as e:
+            scpd.Decoder(args["n"], args["k"], fl, par=args["par"], llr_bits=args["llr_bits"], fmt=args["fmt"],
+                         extended=args["extended"], pruning=args["pruning"])
+        assert e.value.status == scpd.E_CONFIG, kw
+    assert abs(scpd.sigma(2.5, 0.5) - ol.sigma(2.5, 0.5)) < 1e-7
+    assert scpd.lib.scpd_status_string(scpd.E_IO) == b"i/o error"
+    assert scpd.lib.scpd_decode(None, None, 1, None, None) == scpd.E_ARG
