@@ -27,7 +27,9 @@ enum Op : uint32_t {
     OP_H = 4,      // beta[o+i] ^= beta[o+n/2+i], i < n/2                        H_STATE  :903-932
     OP_HCOPY = 5,  // beta[o+i]  = beta[o+n/2+i]   (left child all-frozen: 0 ^ x)
     OP_R0 = 6,     // beta[o..o+n) = 0            (all-frozen node)
-    OP_R1 = 7,     // all-information node: hard decision, plain-SC fallback if an LLR is 0
+    OP_R1 = 7,     // all-information node: hard decision, plain-SC fallback if an LLR is 0.  In fast-kernel
+                   // schedules the next word is the length of the fallback ops that follow (skipped
+                   // when no LLR of the node is 0)
     OP_P2 = 8,     // two-bit terminal, Spec_P2 functions.h:367-384; leaf flags = (f0, f1)
     OP_P1 = 9,     // one-bit terminal, Spec_P1 functions.h:355-364; leaf flag bit0 = f
     OP_SUB = 10,   // register subtree of size 2^l (fast kernel); followed by its node-type words
@@ -90,8 +92,63 @@ struct ScheduleBuilder {
                 words[(2 * heap) >> 5] |= t << ((2 * heap) & 31);
             }
         }
-        ops.push_back(op_make(OP_SUB, l, o));
+        // bit 9: the pattern-specialised small-node routines (which prune internally) may be used
+        ops.push_back(op_make(OP_SUB, l, o, pruning >= 2 ? 1u : 0u));
         for (uint32_t w : words) ops.push_back(w);
+        push_flag_words(l, o, false);
+        push_sub8_words(l, o, false);
+    }
+    // one word per size-8 node of the subtree: the types of its 7 nodes (sizes 8, 4, 4, 2, 2, 2, 2)
+    // in local heap order, 2 bits each, same coding as above
+    void push_sub8_words(int l, uint32_t o, bool all_ones) {
+        for (uint32_t k = 0; k < (1u << l) / 8; k++) {
+            uint32_t w = 0, heap = 0;
+            for (int d = 0; d < 3; d++) {
+                const uint32_t sz = 8u >> d;
+                for (uint32_t j = 0; j < (1u << d); j++, heap++) {
+                    const uint32_t off = o + 8 * k + j * sz;
+                    uint32_t t;
+                    if (all_ones) {
+                        t = 2u;
+                    } else if (sz == 2) {
+                        const uint32_t f0 = flags[off] & 1u, f1 = flags[off + 1] & 1u;
+                        t = (f0 == 0 && f1 == 1) ? 0u : (f0 == 0 && f1 == 0) ? 1u : (f0 == 1 && f1 == 1) ? 2u : 3u;
+                    } else {
+                        const uint32_t c = count(off, sz);
+                        t = (pruning >= 1 && c == 0) ? 1u : (pruning >= 2 && c == sz) ? 2u : 0u;
+                    }
+                    w |= t << (2 * heap);
+                }
+            }
+            ops.push_back(w);
+        }
+    }
+    // raw information flags of the subtree (bit i = element o + i), ceil(2^l / 32) words: lets the
+    // kernel pick a pattern-specialised routine for the small nodes
+    void push_flag_words(int l, uint32_t o, bool all_ones) {
+        const uint32_t sz = 1u << l;
+        for (uint32_t w0 = 0; w0 < sz; w0 += 32) {
+            uint32_t v = 0;
+            for (uint32_t b = 0; b < 32 && w0 + b < sz; b++) v |= (all_ones ? 1u : (flags[o + w0 + b] & 1u)) << b;
+            ops.push_back(v);
+        }
+    }
+
+    // un-pruned walk of an all-information node down to the register subtrees (rate-1 fallback)
+    void emit_plain(int l, uint32_t o) {
+        if (l == log2sub) {
+            const uint32_t nodes = (1u << l) - 1u;
+            ops.push_back(op_make(OP_SUB, l, o, 1u));
+            for (uint32_t w = 0; w < (2 * nodes + 31) / 32; w++) ops.push_back(0xAAAAAAAAu);  // every node type 2
+            push_flag_words(l, o, true);
+            push_sub8_words(l, o, true);
+            return;
+        }
+        ops.push_back(op_make(OP_F, l, o));
+        emit_plain(l - 1, o);
+        ops.push_back(op_make(OP_G, l, o, nosat(l)));
+        emit_plain(l - 1, o + (1u << (l - 1)));
+        ops.push_back(op_make(OP_H, l, o));
     }
 
     void emit(int l, uint32_t o) {
@@ -113,6 +170,12 @@ struct ScheduleBuilder {
         if (pruning >= 2 && c == n) {
             ops.push_back(op_make(OP_R1, l, o));
             st.n_r1++;
+            if (log2sub >= 0) {  // explicit plain-SC fallback of this node, skipped unless an LLR is 0
+                const size_t at = ops.size();
+                ops.push_back(0u);
+                emit_plain(l, o);
+                ops[at] = (uint32_t)(ops.size() - at - 1);
+            }
             return;
         }
         if (l == log2sub) {

@@ -113,6 +113,7 @@ struct scpd_decoder {
     size_t ws_bytes = 0;
     // fast-kernel plan (decode_fast.cuh); fast_group == 0: not available for this configuration
     int fast_group = 0;
+    int fast_warps = 4;
     int fast_log2s = 0;
     std::vector<uint32_t> fast_sched_host;
     ScheduleStats fast_stats;
@@ -177,27 +178,33 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
     }
     if (!k) return SCPD_OK;
     const int log2s = ilog2(8 * g);
-    if (d->log2par > log2s || d->log2n < log2s + 1) return SCPD_OK;  // leaf must sit inside the register subtree
+    if (d->log2par > log2s || d->log2n < log2s + 1 || d->cfg.n < 32) return SCPD_OK;  // leaf must sit inside the register subtree
     d->fast_log2s = log2s;
     d->fast_sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning, flags,
                                         &d->fast_stats, log2s);
+    d->fast_warps = std::max(1, std::min(8, env_int("SCPD_WARPS", 8)));
     const int gpw = 32 / g;
-    const int fp_per_cta = d->warps_per_cta * gpw;
-    const size_t budget = (size_t)env_int("SCPD_SMEM_KB", 56) * 1024;
+    const int fp_per_cta = d->fast_warps * gpw;
+    const size_t budget = (size_t)env_int("SCPD_SMEM_KB", 100) * 1024;
     const size_t per_fp = budget / fp_per_cta;
     const uint32_t n = d->cfg.n;
-    // alpha levels log2s..lsa (cell index (1 << l) + i  ->  2 << lsa cells), then the partial-sum block
-    int lsa = log2s;
-    for (int l = log2s; l <= d->log2n - 1; l++)
-        if ((size_t)(2u << l) * 2 <= per_fp * 6 / 10) lsa = l;
-    const size_t alpha_bytes = (size_t)(2u << lsa) * 2;
-    int lsb = log2s;
-    for (int l = log2s; l <= d->log2n; l++) {
-        const size_t cells = std::min<size_t>((size_t)2u << l, n);
-        if (alpha_bytes + cells * 2 <= per_fp) lsb = l;
+    // Shared memory per frame pair: alpha levels log2s..lsa as cells (level l at cell (1 << l): 2 << lsa
+    // cells), then the partial-sum block (one byte per element, 2^(lsb+1) bytes, at most n).
+    // Start with everything resident and push the largest level out to the workspace until it fits.
+    int lsa = d->log2n - 1, lsb = d->log2n;
+    auto a_bytes = [&](int l) { return (size_t)(2u << l) * 2; };
+    auto b_bytes = [&](int l) { return std::min<size_t>((size_t)2u << l, n); };
+    while (a_bytes(lsa) + b_bytes(lsb) > per_fp && (lsa > log2s || lsb > log2s)) {
+        const size_t drop_a = lsa > log2s ? a_bytes(lsa) - a_bytes(lsa - 1) : 0;
+        const size_t drop_b = lsb > log2s ? b_bytes(lsb) - b_bytes(lsb - 1) : 0;
+        if (drop_a >= drop_b && lsa > log2s)
+            lsa--;
+        else
+            lsb--;
     }
-    const size_t beta_cells = std::min<size_t>((size_t)2u << lsb, n);
-    size_t stride = alpha_bytes + beta_cells * 2;
+    const size_t alpha_bytes = a_bytes(lsa);
+    const size_t beta_bytes = b_bytes(lsb);
+    size_t stride = alpha_bytes + beta_bytes;
     stride = (stride + 127) & ~(size_t)127;
     if (g < 8) stride += 16 * g;  // spread the groups of a quarter-warp over distinct banks
     d->fast_lsa = (uint32_t)lsa;
@@ -205,14 +212,18 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
     d->fast_sm_alpha_cells = (uint32_t)(2u << lsa);
     d->fast_sm_stride = (uint32_t)stride;
     d->fast_smem_bytes = stride * fp_per_cta;
-    d->fast_ws_stride = ((unsigned long long)n * 6ull + 255ull) & ~255ull;
+    d->fast_ws_stride = ((unsigned long long)n * 5ull + 255ull) & ~255ull;  // alpha 4n bytes + partial sums n bytes
     CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->fast_smem_bytes));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, d->warps_per_cta * 32,
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, d->fast_warps * 32,
                                                            d->fast_smem_bytes));
     if (occ < 1) return SCPD_OK;  // does not fit: stay on the generic kernel
     d->fast_ctas_per_sm = occ;
     d->fast_group = g;
+    if (env_int("SCPD_VERBOSE", 0))
+        fprintf(stderr, "[scpd] fast kernel G=%d warps/CTA=%d: alpha levels <=%d and partial sums <=%d in smem, "
+                "%zu B/pair, %zu B/CTA, %d CTAs/SM, workspace %llu B/pair\n", g, d->fast_warps, lsa, lsb, stride,
+                d->fast_smem_bytes, occ, d->fast_ws_stride);
     return SCPD_OK;
 }
 
@@ -337,7 +348,7 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
 
 static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
     const int g = d->fast_group, gpw = 32 / g;
-    const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
+    const unsigned long long fp_per_cta = (unsigned long long)d->fast_warps * gpw;
     const unsigned long long num_fp = (nframes + 1) / 2;
     unsigned long long grid = (num_fp + fp_per_cta - 1) / fp_per_cta;
     const unsigned long long max_grid = (unsigned long long)d->num_sms * d->fast_ctas_per_sm;
@@ -368,7 +379,7 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     p.ws = d->d_fast_ws;
     p.ws_stride = d->fast_ws_stride;
     fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
-    k<<<dim3((unsigned)grid), dim3((unsigned)(d->warps_per_cta * 32)), d->fast_smem_bytes, st>>>(p);
+    k<<<dim3((unsigned)grid), dim3((unsigned)(d->fast_warps * 32)), d->fast_smem_bytes, st>>>(p);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;

@@ -11,6 +11,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __align__(x) __attribute__((aligned(x)))
 #define __shared__

@@ -161,14 +161,14 @@ int emu_fast_decode(int g, int log2n, int log2par, int llr_bits, int extended, i
     p.lsa = (uint32_t)lsa;
     p.lsb = (uint32_t)lsb;
     p.sm_alpha_cells = 2u << lsa;
-    const size_t beta_cells = std::min<size_t>((size_t)2u << lsb, n);
-    size_t stride = ((size_t)p.sm_alpha_cells * 2 + beta_cells * 2 + 127) & ~(size_t)127;
+    const size_t beta_bytes = std::min<size_t>((size_t)2u << lsb, n);
+    size_t stride = ((size_t)p.sm_alpha_cells * 2 + beta_bytes + 127) & ~(size_t)127;
     if (g < 8) stride += 16 * g;
     p.sm_stride = (uint32_t)stride;
     const int gpw = 32 / g;
     const size_t fp_per_cta = (size_t)warps * gpw;
     if (stride * fp_per_cta > sizeof(smem_fast)) return -3;
-    p.ws_stride = ((unsigned long long)n * 6ull + 255ull) & ~255ull;
+    p.ws_stride = ((unsigned long long)n * 5ull + 255ull) & ~255ull;
     std::vector<uint8_t> ws((size_t)grid * fp_per_cta * p.ws_stride + 256, 0xCD);
     p.ws = reinterpret_cast<uint8_t*>(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
     dim3 gd, bd;
