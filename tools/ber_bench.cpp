@@ -1,0 +1,102 @@
+// ber_bench.cpp -- command-line counterpart of the reference testbench (src/testbench/main.cpp):
+// BPSK/AWGN/quantiser -> SC decoder -> error counter, all on the device, through the C ABI.
+// Unlike main.cpp (no arguments, macros), everything is a run-time option.
+//
+//   ber_bench --order FILE | --flags FILE  -n N -k K [--par 16] [--q 8] [--sm] [--no-ext]
+//             [--prune 0|1|2] [--snr 2.5[:step:stop]] [--rate R] [--frames F] [--seed 0xF0] [--device D]
+//             [--gpus G]   (frames split over G devices as independent streams; counters summed)
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/scpd.hpp"
+
+int main(int argc, char** argv) {
+    std::string order, flagsf;
+    uint32_t n = 0, k = 0, par = 16, q = 8, fmt = SCPD_FMT_CA2, ext = 1, prune = SCPD_PRUNE_R0_R1;
+    double snr0 = 2.5, snr_step = 0.0, snr1 = 2.5, rate = -1.0;
+    uint64_t frames = 1 << 16;
+    int seed = 0xF0, device = 0, gpus = 1;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--order") order = next();
+        else if (a == "--flags") flagsf = next();
+        else if (a == "-n") n = (uint32_t)std::strtoul(next(), nullptr, 0);
+        else if (a == "-k") k = (uint32_t)std::strtoul(next(), nullptr, 0);
+        else if (a == "--par") par = (uint32_t)std::strtoul(next(), nullptr, 0);
+        else if (a == "--q") q = (uint32_t)std::strtoul(next(), nullptr, 0);
+        else if (a == "--sm") fmt = SCPD_FMT_SIGMAG;
+        else if (a == "--no-ext") ext = 0;
+        else if (a == "--prune") prune = (uint32_t)std::strtoul(next(), nullptr, 0);
+        else if (a == "--rate") rate = std::atof(next());
+        else if (a == "--frames") frames = std::strtoull(next(), nullptr, 0);
+        else if (a == "--seed") seed = (int)std::strtol(next(), nullptr, 0);
+        else if (a == "--device") device = std::atoi(next());
+        else if (a == "--gpus") gpus = std::atoi(next());
+        else if (a == "--snr") {
+            double v[3] = {2.5, 0, 0};
+            int c = std::sscanf(next(), "%lf:%lf:%lf", &v[0], &v[1], &v[2]);
+            snr0 = v[0];
+            snr_step = c == 3 ? v[1] : 0.0;
+            snr1 = c == 3 ? v[2] : v[0];
+        } else {
+            std::fprintf(stderr, "unknown option %s\n", a.c_str());
+            return 2;
+        }
+    }
+    if (!n || (order.empty() && flagsf.empty())) {
+        std::fprintf(stderr, "usage: ber_bench (--order FILE -k K | --flags FILE) -n N [options]\n");
+        return 2;
+    }
+    try {
+        std::vector<uint8_t> flags = order.empty() ? scpd::load_flag_table(flagsf, n, &k) : scpd::load_order_table(order, n, k);
+        if (rate <= 0) rate = double(k) / double(n);  // the reference hard-codes R = 0.5 (main.cpp:92)
+        scpd_config cfg{n, k, par, q, fmt, ext, prune, 0};
+        std::printf("(II) Frame size %u, K %u, LLR width %u, QUANT [4, -31, 31], PAR %u, %s, EXTENDED %u, %d GPU(s)\n", n, k,
+                    q, par, fmt == SCPD_FMT_CA2 ? "CA2" : "SIGMAG", ext, gpus);
+        for (double snr = snr0; snr <= snr1 + 1e-9; snr += (snr_step > 0 ? snr_step : 1e9)) {
+            std::vector<scpd::BerCounters> part(gpus);
+            std::vector<std::string> errs(gpus);
+            const auto t0 = std::chrono::steady_clock::now();
+            std::vector<std::thread> th;
+            for (int g = 0; g < gpus; g++) {
+                th.emplace_back([&, g] {
+                    try {
+                        const uint64_t lo = frames * g / gpus, hi = frames * (g + 1) / gpus;
+                        scpd::PolarDecoder dec(cfg, flags, device + g);  // one handle, one stream per GPU; no collective
+                        part[g] = dec.run_ber((float)snr, (float)rate, hi - lo, lo, (uint8_t)seed);
+                    } catch (const std::exception& e) {
+                        errs[g] = e.what();
+                    }
+                });
+            }
+            for (auto& t : th) t.join();
+            for (auto& e : errs)
+                if (!e.empty()) throw std::runtime_error(e);
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            scpd::BerCounters c{0, 0, 0, 0, 0, 0};
+            for (auto& p : part) {  // the only "reduction" of the path: four (six) 64-bit counters per GPU
+                c.bit_errors += p.bit_errors;
+                c.frame_errors += p.frame_errors;
+                c.bits += p.bits;
+                c.frames += p.frames;
+                c.bit_errors_wrapped += p.bit_errors_wrapped;
+                c.frame_errors_wrapped += p.frame_errors_wrapped;
+            }
+            std::printf("Eb/N0 %.2f dB sigma %.4f | FRA %llu BE %llu FE %llu | BER %.3e FER %.3e | %.2f Gb/s info (incl. channel)\n",
+                        snr, scpd_sigma((float)snr, (float)rate), (unsigned long long)c.frames,
+                        (unsigned long long)c.bit_errors, (unsigned long long)c.frame_errors, c.ber(), c.fer(),
+                        double(c.frames) * k / sec / 1e9);
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
