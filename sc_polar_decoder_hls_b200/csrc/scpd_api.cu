@@ -206,7 +206,10 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
     const size_t beta_bytes = b_bytes(lsb);
     size_t stride = alpha_bytes + beta_bytes;
     stride = (stride + 127) & ~(size_t)127;
-    if (g < 8) stride += 16 * g;  // spread the groups of a quarter-warp over distinct banks
+    {   // spread the groups of a warp over distinct banks (SCPD_BANK_PAD overrides, bytes)
+        const int pad = env_int("SCPD_BANK_PAD", g < 8 ? 16 * g : 32);
+        stride += (size_t)pad;
+    }
     d->fast_lsa = (uint32_t)lsa;
     d->fast_lsb = (uint32_t)lsb;
     d->fast_sm_alpha_cells = (uint32_t)(2u << lsa);
