@@ -19,19 +19,39 @@ def _newest_source_mtime():
     return t
 
 
+STAMP = os.path.join(HERE, "libscpd.flavour")
+
+
+def _flavour():
+    return "fast" if os.environ.get("SCPD_FAST_BUILD") else "full"
+
+
+def _stamp():
+    try:
+        return open(STAMP).read().strip()
+    except OSError:
+        return ""
+
+
 def build_lib(force=False, verbose=False):
-    """Compile every CUDA source of the package into libscpd.so. Returns the library path."""
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+    """Compile every CUDA source of the package into libscpd.so. Returns the library path.
+    SCPD_FAST_BUILD=1 (development) leaves out most template instantiations; a library built that way
+    is rebuilt in full the next time the variable is not set."""
+    if (not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime()
+            and _stamp() == _flavour()):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         if os.path.exists(LIB):
             return LIB  # GPU box without a toolkit: use the library that travelled with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt libscpd.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = ["-DSCPD_FAST_BUILD"] if os.environ.get("SCPD_FAST_BUILD") else []  # development: fewer instantiations
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout)
+    with open(STAMP, "w") as f:
+        f.write(_flavour() + "\n")
     if verbose:
         print(r.stdout)
     return LIB
@@ -42,7 +62,7 @@ def wait_for_lib(timeout=600.0):
     import time
     t0 = time.time()
     while time.time() - t0 < timeout:
-        if os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+        if os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime() and _stamp() == _flavour():
             time.sleep(0.5)
             return LIB
         time.sleep(0.5)

@@ -56,6 +56,11 @@ struct ScheduleStats {
 struct ScheduleBuilder {
     int log2n, log2par, extended, pruning;
     int log2sub = -1;  // >= 0: stop at nodes of this size and emit OP_SUB + descriptor (fast kernel)
+    // bit-sliced kernel: 1 = every OP_R1 is followed by a skip count and by the plain-SC ops of the node
+    // whose children are OP_R1 again (a zero LLR only unfolds the path it sits on); 2 = skip count 0 and
+    // no fallback ops (SIGMAG, where the hard decision is always identical to plain SC)
+    int r1_mode = 0;
+    bool bs_sub = false;  // OP_SUB carries only the node-type words (bit-sliced kernel)
     const uint8_t* flags;
     std::vector<uint32_t> psum;  // prefix sums of flags
     std::vector<uint32_t> ops;
@@ -95,6 +100,7 @@ struct ScheduleBuilder {
         // bit 9: the pattern-specialised small-node routines (which prune internally) may be used
         ops.push_back(op_make(OP_SUB, l, o, pruning >= 2 ? 1u : 0u));
         for (uint32_t w : words) ops.push_back(w);
+        if (bs_sub) return;
         push_flag_words(l, o, false);
         push_sub8_words(l, o, false);
     }
@@ -151,6 +157,29 @@ struct ScheduleBuilder {
         ops.push_back(op_make(OP_H, l, o));
     }
 
+    // all-information node of the bit-sliced schedules (r1_mode 1 / 2)
+    void emit_r1_tree(int l, uint32_t o) {
+        if (l == log2sub) {  // the fused subtree routine does its own hard decision / zero vote
+            emit_subtree(l, o);
+            return;
+        }
+        if (l == 1) {
+            ops.push_back(op_make(OP_P2, 1, o, 0, 3u));
+            return;
+        }
+        ops.push_back(op_make(OP_R1, l, o));
+        st.n_r1++;
+        const size_t at = ops.size();
+        ops.push_back(0u);
+        if (r1_mode == 2) return;
+        ops.push_back(op_make(OP_F, l, o));
+        emit_r1_tree(l - 1, o);
+        ops.push_back(op_make(OP_G, l, o, nosat(l)));
+        emit_r1_tree(l - 1, o + (1u << (l - 1)));
+        ops.push_back(op_make(OP_H, l, o));
+        ops[at] = (uint32_t)(ops.size() - at - 1);
+    }
+
     void emit(int l, uint32_t o) {
         const uint32_t n = 1u << l;
         const uint32_t c = count(o, n);
@@ -165,6 +194,10 @@ struct ScheduleBuilder {
         }
         if (l == 1 && log2par >= 1) {
             ops.push_back(op_make(OP_P2, 1, o, 0, (flags[o] & 1u) | ((flags[o + 1] & 1u) << 1)));
+            return;
+        }
+        if (pruning >= 2 && c == n && r1_mode != 0) {
+            emit_r1_tree(l, o);
             return;
         }
         if (pruning >= 2 && c == n) {
@@ -211,9 +244,11 @@ struct ScheduleBuilder {
 // flags: n bytes, 1 = information bit.  Returns the op list terminated by OP_END.
 static inline std::vector<uint32_t> build_schedule(int log2n, int log2par, int extended, int pruning,
                                                    const uint8_t* flags, ScheduleStats* stats,
-                                                   int log2sub = -1) {
+                                                   int log2sub = -1, int r1_mode = 0) {
     ScheduleBuilder b;
     b.log2sub = log2sub;
+    b.r1_mode = r1_mode;
+    b.bs_sub = r1_mode != 0;
     b.log2n = log2n;
     b.log2par = log2par;
     b.extended = extended;
@@ -224,6 +259,7 @@ static inline std::vector<uint32_t> build_schedule(int log2n, int log2par, int e
     for (uint32_t i = 0; i < n; i++) b.psum[i + 1] = b.psum[i] + (flags[i] ? 1u : 0u);
     b.emit(log2n, 0);
     b.ops.push_back(op_make(OP_END, 0, 0));
+    b.ops.push_back(op_make(OP_END, 0, 0));  // kernels prefetch one word ahead
     b.st.n_ops = b.ops.size();
     if (stats) *stats = b.st;
     return b.ops;

@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "../../include/scpd.h"
+#include "bs_plan.h"
+#include "decode_bs.cuh"
 #include "decode_fast.cuh"
 #include "decode_generic.cuh"
 #include "harness.cuh"
@@ -124,6 +126,17 @@ struct scpd_decoder {
     int fast_ctas_per_sm = 1;
     uint8_t* d_fast_ws = nullptr;
     size_t fast_ws_bytes = 0;
+    // bit-sliced kernel plan (decode_bs.cuh); bs_ok == false: not available for this configuration
+    bool bs_ok = false;
+    int bs_group = 8, bs_warps = 2, bs_ctas_per_sm = 1;
+    bool bs_sched_smem = false;
+    BsPlan bs_plan;
+    std::vector<uint32_t> bs_sched_host;
+    ScheduleStats bs_stats;
+    uint32_t* d_bs_sched = nullptr;
+    size_t bs_smem_bytes = 0;
+    uint8_t* d_bs_ws = nullptr;
+    size_t bs_ws_bytes = 0;
     // staging for scpd_decode_host / scpd_run_ber
     int8_t* d_llr = nullptr;
     uint32_t* d_xhat = nullptr;
@@ -162,6 +175,68 @@ static fast_kernel_t fast_kernel_ptr(int group, int log2par, int ext) {
 static int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
+}
+
+typedef void (*bs_kernel_t)(const BsParams);
+// Instantiated (format, LLR_BITS, log2 PAR, EXTENDED, lanes per frame group) combinations of the
+// bit-sliced kernel.  g == 0: "is there any instantiation for this configuration".
+static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
+#define BS_K(F, Q, LP, E, GG)                                                                  \
+    if (fmt == F && q == Q && log2par == LP && ext == (E ? 1 : 0) && (g == GG || g == 0)) \
+        return sc_decode_bs_kernel<F, Q, LP, E, GG>;
+    BS_K(0, 8, 4, true, 8)
+    BS_K(0, 8, 4, true, 16)
+    BS_K(0, 8, 4, true, 32)
+#ifndef SCPD_FAST_BUILD
+    BS_K(0, 8, 4, false, 8)
+    BS_K(0, 6, 4, true, 8)
+    BS_K(1, 6, 4, true, 8)
+    BS_K(1, 6, 4, false, 8)
+    BS_K(1, 8, 4, true, 8)
+#endif
+#undef BS_K
+    return nullptr;
+}
+
+// Decide whether the bit-sliced kernel applies and lay out its shared memory / workspace.
+static int plan_bs(scpd_decoder* d, const uint8_t* flags) {
+    d->bs_ok = false;
+    const char* ksel = std::getenv("SCPD_KERNEL");
+    if (ksel && std::strcmp(ksel, "bs") != 0 && d->cfg.format == SCPD_FMT_CA2) return SCPD_OK;
+    int g = env_int("SCPD_BS_GROUP", 8);
+    bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, g);
+    if (!k) {
+        g = 8;
+        k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, g);
+    }
+    if (!k || d->log2n < 7) return SCPD_OK;
+    d->bs_group = g;
+    d->bs_warps = std::max(1, std::min(16, env_int("SCPD_BS_WARPS", 8)));
+    const size_t per_group = (size_t)env_int("SCPD_BS_SMEM_KB", 13) * 1024;
+    if (!bs_make_plan(d->log2n, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, per_group, &d->bs_plan,
+                      env_int("SCPD_BS_LSA", -1), env_int("SCPD_BS_LSB", -1), g))
+        return SCPD_OK;
+    {
+        const std::vector<uint32_t> ops = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning,
+                                                         flags, &d->bs_stats, BS_LSUB, d->cfg.format == SCPD_FMT_CA2 ? 1 : 2);
+        if (!bs_compile_schedule(ops, &d->bs_sched_host, env_int("SCPD_BS_SYNC", 1))) return SCPD_OK;
+    }
+    // a schedule of up to 8 KB is copied into shared memory by every CTA (op fetches then never miss)
+    d->bs_sched_smem = d->bs_sched_host.size() <= (size_t)env_int("SCPD_BS_SCHED_SMEM_WORDS", 2048);
+    d->bs_smem_bytes = (size_t)d->bs_plan.sm_stride * d->bs_warps * (32 / g) +
+                       (d->bs_sched_smem ? d->bs_sched_host.size() * 4 : 0);
+    if (d->bs_smem_bytes > 227 * 1024) return SCPD_OK;
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bs_smem_bytes));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, d->bs_warps * 32, d->bs_smem_bytes));
+    if (occ < 1) return SCPD_OK;
+    d->bs_ctas_per_sm = occ;
+    d->bs_ok = true;
+    if (env_int("SCPD_VERBOSE", 0))
+        fprintf(stderr, "[scpd] bit-sliced kernel: %d lanes/group, %d warps/CTA, alpha levels <=%u and partial sums <=%u "
+                "in smem, %u B/group, %d CTAs/SM, workspace %llu B/group, %zu schedule words\n", g, d->bs_warps, d->bs_plan.lsa,
+                d->bs_plan.lsb, d->bs_plan.sm_stride, occ, d->bs_plan.ws_stride, d->bs_sched_host.size());
+    return SCPD_OK;
 }
 
 // Decide whether the fast kernel applies and size its shared-memory / workspace layout.
@@ -284,8 +359,6 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     if (cfg->extended > 1) return set_error(SCPD_E_CONFIG, "extended must be 0 or 1");
     if (cfg->llr_bits < 5 || cfg->llr_bits > 9)
         return set_error(SCPD_E_CONFIG, "llr_bits outside 5..9 (range swept by script/script_tests.sh)");
-    if (cfg->format == SCPD_FMT_SIGMAG)
-        return set_error(SCPD_E_UNSUPPORTED, "SIGMAG arithmetic has no kernel in this build yet");
     if (cfg->llr_bits < 6)
         return set_error(SCPD_E_UNSUPPORTED,
                          "llr_bits < 6: the +-31 quantiser alphabet wraps in the reference; no kernel for that yet");
@@ -293,6 +366,10 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     // widest value inside the un-saturated leaf must fit int16 (Q + log2 PAR bits incl. the final sum)
     if (cfg->extended && cfg->llr_bits + (uint32_t)log2par > 16)
         return set_error(SCPD_E_UNSUPPORTED, "llr_bits + log2(par) > 16 does not fit the int16x2 datapath");
+    if (cfg->format == SCPD_FMT_SIGMAG &&
+        (!bs_kernel_ptr(SCPD_FMT_SIGMAG, (int)cfg->llr_bits, log2par, (int)cfg->extended, 0) || n < 128))
+        return set_error(SCPD_E_UNSUPPORTED,
+                         "SIGMAG: no bit-sliced kernel instantiated for this (llr_bits, par, extended) or n < 128");
 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
@@ -313,6 +390,9 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     d->num_sms = prop.multiProcessorCount;
     int rc = plan_layout(d);
     if (rc == SCPD_OK) rc = plan_fast(d, flags);
+    if (rc == SCPD_OK) rc = plan_bs(d, flags);
+    if (rc == SCPD_OK && cfg->format == SCPD_FMT_SIGMAG && !d->bs_ok)
+        rc = set_error(SCPD_E_UNSUPPORTED, "SIGMAG: the bit-sliced kernel does not fit this configuration");
     if (rc != SCPD_OK) {
         delete d;
         return rc;
@@ -325,6 +405,12 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
         e = cudaMalloc(&d->d_fast_sched, d->fast_sched_host.size() * sizeof(uint32_t));
         if (e == cudaSuccess)
             e = cudaMemcpy(d->d_fast_sched, d->fast_sched_host.data(), d->fast_sched_host.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && d->bs_ok) {
+        e = cudaMalloc(&d->d_bs_sched, d->bs_sched_host.size() * sizeof(uint32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(d->d_bs_sched, d->bs_sched_host.data(), d->bs_sched_host.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess) e = cudaMalloc(&d->d_counters, 6 * sizeof(unsigned long long));
@@ -343,6 +429,8 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_ws);
     cudaFree(d->d_fast_sched);
     cudaFree(d->d_fast_ws);
+    cudaFree(d->d_bs_sched);
+    cudaFree(d->d_bs_ws);
     cudaFree(d->d_llr);
     cudaFree(d->d_xhat);
     cudaFree(d->d_counters);
@@ -388,12 +476,55 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     return SCPD_OK;
 }
 
+static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
+    const unsigned long long ngroups = (nframes + 31) / 32;
+    const unsigned long long gpc = (unsigned long long)d->bs_warps * (32 / d->bs_group);  // groups per CTA
+    unsigned long long grid = (ngroups + gpc - 1) / gpc;
+    const unsigned long long max_grid = (unsigned long long)d->num_sms * d->bs_ctas_per_sm;
+    if (grid > max_grid) grid = max_grid;
+    const size_t ws_need = (size_t)(grid * gpc * d->bs_plan.ws_stride);
+    if (ws_need > d->bs_ws_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_bs_ws);
+        d->d_bs_ws = nullptr;
+        d->bs_ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&d->d_bs_ws, ws_need));
+        d->bs_ws_bytes = ws_need;
+    }
+    BsParams p;
+    p.sched = d->d_bs_sched;
+    p.sched_words = d->bs_sched_smem ? (uint32_t)d->bs_sched_host.size() : 0u;
+    p.llr = d_llr;
+    p.xhat = d_xhat;
+    p.nframes = nframes;
+    p.ngroups = ngroups;
+    p.n = d->cfg.n;
+    p.log2n = (uint32_t)d->log2n;
+    p.wpf = d->wpf;
+    p.lsa = d->bs_plan.lsa;
+    p.lsb = d->bs_plan.lsb;
+    p.sm_stride = d->bs_plan.sm_stride;
+    p.sm_beta_off = d->bs_plan.sm_beta_off;
+    p.ws = d->d_bs_ws;
+    p.ws_stride = d->bs_plan.ws_stride;
+    p.ws_beta_off = d->bs_plan.ws_beta_off;
+    for (int l = 0; l < 24; l++) p.aoff[l] = d->bs_plan.aoff[l];
+    bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->bs_group);
+    k<<<dim3((unsigned)grid), dim3((unsigned)(d->bs_warps * 32)), d->bs_smem_bytes, st>>>(p);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
 extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, void* stream) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_decode: null decoder");
     if (nframes == 0) return SCPD_OK;
     if (!d_llr || !d_xhat) return set_error(SCPD_E_ARG, "scpd_decode: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->bs_ok && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0) return decode_bs(d, d_llr, nframes, d_xhat, st);
+    if (d->cfg.format != SCPD_FMT_CA2)
+        return set_error(SCPD_E_ARG, "scpd_decode: SIGMAG needs a 4-byte aligned LLR buffer");
     if (d->fast_group && (reinterpret_cast<uintptr_t>(d_llr) & 7u) == 0) return decode_fast(d, d_llr, nframes, d_xhat, st);
     const int gpw = 32 / d->group;
     const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
@@ -486,7 +617,7 @@ extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
 }
 extern "C" int scpd_schedule_stats(const scpd_decoder* d, uint64_t* n_ops, uint64_t* n_fg) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_schedule_stats: null decoder");
-    const ScheduleStats& st = d->fast_group ? d->fast_stats : d->stats;
+    const ScheduleStats& st = d->bs_ok ? d->bs_stats : d->fast_group ? d->fast_stats : d->stats;
     if (n_ops) *n_ops = st.n_ops;
     if (n_fg) *n_fg = st.n_f + st.n_g;
     return SCPD_OK;

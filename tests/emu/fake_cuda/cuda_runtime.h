@@ -42,6 +42,8 @@ static inline T __ldg(const T* p) { return *p; }
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cuda_emu::collective_sync(); }
+// the emulator runs the warps of a CTA one after the other; kernels must not rely on this under emulation
+static inline void __syncthreads() { cuda_emu::collective_sync(); }
 static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src, int width = 32) {
     const int lane = cuda_emu::cur->lane;
     return cuda_emu::collective_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));

@@ -11,6 +11,8 @@
 #include "cuda_runtime.h"
 // keep this include after the fake runtime
 #include "../../sc_polar_decoder_hls_b200/csrc/decode_fast.cuh"
+#include "../../sc_polar_decoder_hls_b200/csrc/decode_bs.cuh"
+#include "../../sc_polar_decoder_hls_b200/csrc/bs_plan.h"
 
 namespace scpd {
 __attribute__((aligned(16))) uint8_t smem_fast[232448];
@@ -170,6 +172,64 @@ int emu_fast_decode(int g, int log2n, int log2par, int llr_bits, int extended, i
     if (stride * fp_per_cta > sizeof(smem_fast)) return -3;
     p.ws_stride = ((unsigned long long)n * 5ull + 255ull) & ~255ull;
     std::vector<uint8_t> ws((size_t)grid * fp_per_cta * p.ws_stride + 256, 0xCD);
+    p.ws = reinterpret_cast<uint8_t*>(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
+    dim3 gd, bd;
+    gd.x = (unsigned)grid;
+    bd.x = (unsigned)warps * 32;
+    for (int b = 0; b < grid; b++) {
+        std::memset(smem_fast, 0xEE, sizeof(smem_fast));
+        dim3 bi;
+        bi.x = (unsigned)b;
+        for (int w = 0; w < warps; w++) cuda_emu::run_warp(body, &L, bi, gd, bd, w);
+    }
+    return 0;
+}
+
+// Emulates the bit-sliced kernel (decode_bs.cuh).  fmt 0 = CA2, 1 = SIGMAG; g = lanes per frame group.
+// lsa/lsb < 0: planned from smem_per_group.  Returns 0, -1 if the variant is not compiled into the
+// emulator, -3 if it does not fit.
+int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int extended, int pruning, const uint8_t* flags,
+                  const int8_t* llr, size_t nframes, uint32_t* xhat, int lsa, int lsb, int smem_per_group, int warps,
+                  int grid) {
+    struct BL {
+        BsParams p;
+    } L;
+    void (*body)(void*) = nullptr;
+#define BCASE(F, Q, LP, E, GG)                                                                    \
+    if (fmt == F && llr_bits == Q && log2par == LP && extended == (E ? 1 : 0) && g == GG)         \
+        body = [](void* a) { sc_decode_bs_kernel<F, Q, LP, E, GG>(static_cast<BL*>(a)->p); };
+    BCASE(0, 8, 4, true, 32) BCASE(0, 8, 4, true, 16) BCASE(0, 8, 4, true, 8) BCASE(0, 8, 4, false, 8)
+    BCASE(0, 6, 4, true, 16) BCASE(0, 8, 2, true, 32) BCASE(0, 7, 6, true, 8) BCASE(1, 6, 4, true, 8)
+    BCASE(1, 8, 4, true, 32) BCASE(1, 6, 4, false, 16) BCASE(1, 7, 6, true, 32) BCASE(0, 8, 1, true, 8)
+#undef BCASE
+    if (!body) return -1;
+    if (log2n < 7) return -2;
+    ScheduleStats st;
+    std::vector<uint32_t> ops = build_schedule(log2n, log2par, extended, pruning, flags, &st, BS_LSUB, fmt == 0 ? 1 : 2);
+    std::vector<uint32_t> sched;
+    if (!bs_compile_schedule(ops, &sched)) return -4;
+    BsPlan plan;
+    if (!bs_make_plan(log2n, llr_bits, log2par, extended, (size_t)smem_per_group, &plan, lsa, lsb, g)) return -3;
+    const int gpw = 32 / g;
+    if ((size_t)plan.sm_stride * warps * gpw > sizeof(smem_fast)) return -3;
+    BsParams& p = L.p;
+    p.sched = sched.data();
+    p.sched_words = 0;  // the emulator runs the warps of a CTA one after the other: no __syncthreads
+    p.llr = llr;
+    p.xhat = xhat;
+    p.nframes = nframes;
+    p.ngroups = (nframes + 31) / 32;
+    p.n = 1u << log2n;
+    p.log2n = (uint32_t)log2n;
+    p.wpf = p.n / 32;
+    p.lsa = plan.lsa;
+    p.lsb = plan.lsb;
+    p.sm_stride = plan.sm_stride;
+    p.sm_beta_off = plan.sm_beta_off;
+    p.ws_stride = plan.ws_stride;
+    p.ws_beta_off = plan.ws_beta_off;
+    for (int l = 0; l < 24; l++) p.aoff[l] = plan.aoff[l];
+    std::vector<uint8_t> ws((size_t)grid * warps * gpw * plan.ws_stride + 256, 0xCD);
     p.ws = reinterpret_cast<uint8_t*>(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
     dim3 gd, bd;
     gd.x = (unsigned)grid;

@@ -1,0 +1,73 @@
+"""CPU tier for the bit-sliced kernel (csrc/decode_bs.cuh, bs_arith.cuh): the kernel source executed lane
+by lane under the warp emulator (tests/emu/warp_emu.cpp) against the oracle, in both number formats."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sc_polar_decoder_hls_b200 as scpd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = {}
+
+
+def _emu():
+    if "l" not in _LIB:
+        _LIB["l"] = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libwarp_emu.so"))
+    return _LIB["l"]
+
+
+def bs_emu(fmt, g, flags, n, par, q, ext, prune, llr, lsa=-1, lsb=-1, smem=56000, warps=1, grid=1):
+    out = np.zeros((len(llr), n // 32), np.uint32)
+    rc = _emu().emu_bs_decode(fmt, g, int(np.log2(n)), int(np.log2(par)), q, ext, prune, ol.P(flags), ol.P(llr),
+                              ctypes.c_size_t(len(llr)), ol.P(out), lsa, lsb, smem, warps, grid)
+    assert rc == 0, rc
+    return out
+
+
+# (format, LLR_BITS, PAR, EXTENDED, lanes per frame group) instantiated in the emulator
+VARIANTS = [(0, 8, 16, 1, 32), (0, 8, 16, 1, 16), (0, 8, 16, 1, 8), (0, 8, 16, 0, 8), (0, 6, 16, 1, 16),
+            (1, 6, 16, 1, 8), (1, 8, 16, 1, 32), (1, 6, 16, 0, 16), (0, 7, 64, 1, 8), (1, 7, 64, 1, 32),
+            (0, 8, 2, 1, 8)]
+
+
+@pytest.mark.parametrize("fmt,q,par,ext,g", VARIANTS)
+def test_bs_kernel_source_under_warp_emulator(fmt, q, par, ext, g):
+    """Plane arithmetic (f, saturating / un-saturated g, 2-bit terminals), width growth inside the leaf
+    decoder, fused 16-LLR subtree walk, every pruning mode, ragged last group, CA2 zero fallback."""
+    n, k = 512, 256
+    flags = scpd.packed_flags("FB_N512_K256", n)
+    rng = np.random.default_rng(100 * fmt + q + par + g)
+    llr = ol.test_llrs(rng, n, 70, k, maxabs=min(31, (1 << (q - 1)) - 1))
+    llr[-1][rng.random(n) < 0.5] = 0
+    llr[-2] = 0
+    want = ol.decode_packed(n, par, q, fmt, ext, flags, llr)
+    for prune in (0, 1, 2):
+        assert (bs_emu(fmt, g, flags, n, par, q, ext, prune, llr) == want).all(), prune
+
+
+@pytest.mark.parametrize("name,n,k", [("FB_N1024_K512", 1024, 512), ("frozen_n_4096_k_3072", 4096, 3072)])
+def test_bs_kernel_storage_split_and_grid(name, n, k):
+    """Alpha levels / partial sums pushed out to the workspace, several warps and CTAs, full-range LLRs."""
+    flags = scpd.packed_flags(name, n)
+    rng = np.random.default_rng(n)
+    for g, lsa, lsb, warps, grid, nfr in ((32, 6, 6, 1, 1, 33), (8, 7, 6, 2, 2, 250), (16, 8, 9, 2, 1, 97)):
+        llr = ol.test_llrs(rng, n, nfr, k, maxabs=127)
+        llr[-1][rng.random(n) < 0.5] = 0
+        want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+        got = bs_emu(0, g, flags, n, 16, 8, 1, 2, llr, lsa, lsb, 50000, warps, grid)
+        assert (got == want).all(), (g, lsa, lsb)
+
+
+def test_bs_kernel_random_flag_tables():
+    rng = np.random.default_rng(12)
+    for n in (128, 256):
+        for _ in range(5):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-31, 32, size=(40, n)).astype(np.int8)
+            for fmt, q, g in ((0, 8, 16), (1, 6, 8)):
+                want = ol.decode_packed(n, 16, q, fmt, 1, flags, llr)
+                for prune in (0, 2):
+                    assert (bs_emu(fmt, g, flags, n, 16, q, 1, prune, llr) == want).all(), (n, fmt, prune)

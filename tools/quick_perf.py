@@ -20,6 +20,7 @@ ap.add_argument("--cfg", default="c1")
 ap.add_argument("--frames", type=int, default=1 << 16)
 ap.add_argument("--prune", type=int, default=2)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--check", type=int, default=0, help="verify this many frames against the oracle")
 a = ap.parse_args()
 name, n, k, snr = SETS[a.cfg]
 flags = scpd.packed_flags(name, n)
@@ -29,6 +30,13 @@ out = torch.empty((a.frames, n // 32), dtype=torch.int32, device="cuda")
 for _ in range(2):
     dec.decode(llr, out)
 torch.cuda.synchronize()
+if a.check:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import oracle_lib as ol
+    idx = np.unique(np.concatenate([np.arange(min(a.check, a.frames)), np.arange(max(0, a.frames - a.check), a.frames)]))
+    got = out.cpu().numpy().view(np.uint32)[idx]
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr.cpu().numpy()[idx], threads=8)
+    print("check", len(idx), "frames:", "OK" if (got == want).all() else "MISMATCH")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.iters):
