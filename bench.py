@@ -156,7 +156,7 @@ def run_reference_arm(a):
     sample = f"{nfr} frames N={CFG['n']} K={CFG['k']} per step, decode only, {cores} host processes"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int16", "data": "synthetic",
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: N=4096 K=3072 plain SC, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB",
                        "frames_per_step": nfr, "flush": "n/a (host)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -219,6 +219,15 @@ def run_gpu_arm(a):
     e1.record()
     barrier()
     launches = dec.launches - launches0
+    # duration of the dominant (tree-walk) kernel alone: CUDA events recorded by the library on the stream
+    # the kernel is launched on, averaged over extra launches outside the timed region above
+    dec.kernel_timing(True)
+    kms = []
+    for _ in range(a.steps):
+        dec.decode(llr, xhat)
+        kms.append(dec.last_kernel_ms())
+    dec.kernel_timing(False)
+    kernel_ms = float(np.mean(kms))
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     ms_step = ms_total / a.steps
@@ -251,7 +260,12 @@ def run_gpu_arm(a):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = (hi - lo) * (n + n // 8)  # int8 LLR in + packed x^ out per frame
-        ach = alg_bytes / (ms_step * 1e-3) / 1e9
+        ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        # instruction roofline of SURVEY 8d: I(N) = (N/2) log2 N (7/4 + 1/32) lane-instructions per frame
+        # against the measured 62 lane-instr/clk/SM of the packed-integer / LOP3 pipe (profiles/)
+        lane_instr = (hi - lo) * (n / 2) * np.log2(n) * (7 / 4 + 1 / 32)
+        alu_peak = 148 * 62.0 * 1.965e9
+        alu_frac = lane_instr / (kernel_ms * 1e-3) / alu_peak
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
@@ -265,16 +279,21 @@ def run_gpu_arm(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int16", "data": "synthetic",
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: N=4096 K=3072 plain SC, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB",
+                       "kernel": dec.kernel_name, "arithmetic": "bit-sliced: one u32 = one bit plane of an LLR for 32 frames",
                        "frames_per_step_per_gpu": hi - lo, "frames_per_s": world * (hi - lo) / (ms_step * 1e-3),
                        "coded_gbps": value * n / k, "schedule_ops": ops, "fg_updates_per_frame": fg,
                        "flush": "inputs (4 GiB of LLRs per GPU) larger than the 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic,
+                         "traffic": traffic, "kernel": "sc_decode_bs_kernel", "kernel_ms": kernel_ms,
+                         "kernel_share_of_step": kernel_ms / ms_step,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "note": "decode is integer-ALU bound: see DESIGN.md for the instruction roofline"},
+                         "alu": {"model_lane_instr_per_frame": lane_instr / (hi - lo), "peak_lane_instr_per_s": alu_peak,
+                                 "frac": alu_frac},
+                         "note": "algorithmic bytes are N + N/8 per frame; the kernel is bound by the integer/LOP3 pipe, "
+                                 "L1 and the spilled LLR levels together (DESIGN.md section 6)"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{nfr_cpu} frames of the same batch, decode only, {cores} threads"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((hi - lo) * n),

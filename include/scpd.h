@@ -95,7 +95,8 @@ void scpd_destroy(scpd_decoder* dec);
  * d_llr  : [nframes][n] int8, device.      d_xhat : [nframes][n/32] uint32, device. */
 int scpd_decode(scpd_decoder* dec, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat,
                 void* cuda_stream);
-/* Same through host buffers (pinned or pageable): H2D copy, decode, D2H copy, stream sync.
+/* Same through host buffers (pinned or pageable): the batch is cut into chunks that flow through an
+ * H2D copy / decode / D2H copy pipeline on three streams; returns when h_xhat is complete.
  * This is the call a host-only caller such as the reference testbench would make. */
 int scpd_decode_host(scpd_decoder* dec, const int8_t* h_llr, size_t nframes, uint32_t* h_xhat);
 /* Information-bit estimate u^ = x^ * F^(x)n (extra; the reference outputs x^ only). */
@@ -107,6 +108,13 @@ int scpd_get_config(const scpd_decoder* dec, scpd_config* out);
 int scpd_schedule_stats(const scpd_decoder* dec, uint64_t* n_ops, uint64_t* n_fg_updates);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 uint64_t scpd_launch_count(const scpd_decoder* dec);
+/* Measurement aids (the reference's sc_monitor.h:50-441 counts cycles per FSM state; here the unit is
+ * the decode kernel): with timing enabled every scpd_decode brackets its tree-walk kernel with CUDA
+ * events on the caller's stream; scpd_last_kernel_ms waits for the last one and returns its duration. */
+int scpd_kernel_timing(scpd_decoder* dec, int enable);
+int scpd_last_kernel_ms(scpd_decoder* dec, float* ms);
+/* Which kernel family and layout this handle launches (static text, valid until the next call). */
+const char* scpd_kernel_name(const scpd_decoder* dec);
 
 /* ---- testbench harness on the device: src/testbench/ ---- */
 /* sigma = 1/sqrt(2 R 10^(EbN0/10)), main.cpp:91-98 (the reference hard-codes R = 0.5). */

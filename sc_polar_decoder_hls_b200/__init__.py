@@ -53,6 +53,9 @@ def _load():
         "scpd_get_config": (c.c_int, [vp, c.POINTER(Config)]),
         "scpd_schedule_stats": (c.c_int, [vp, c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]),
         "scpd_launch_count": (c.c_uint64, [vp]),
+        "scpd_kernel_timing": (c.c_int, [vp, c.c_int]),
+        "scpd_last_kernel_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
+        "scpd_kernel_name": (c.c_char_p, [vp]),
         "scpd_sigma": (c.c_float, [c.c_float, c.c_float]),
         "scpd_channel_generate": (c.c_int, [c.c_uint32, c.c_uint64, c.c_size_t, c.c_uint8, c.c_float, vp,
                                             c.c_int, vp, vp]),
@@ -73,7 +76,8 @@ lib = _load()
 EXPORTS = ["scpd_frozen_load_order", "scpd_frozen_load_flags", "scpd_frozen_write_order",
            "scpd_frozen_write_flags", "scpd_write_polar_parameters", "scpd_create", "scpd_destroy",
            "scpd_decode", "scpd_decode_host", "scpd_extract_info", "scpd_get_config",
-           "scpd_schedule_stats", "scpd_launch_count", "scpd_sigma", "scpd_channel_generate",
+           "scpd_schedule_stats", "scpd_launch_count", "scpd_kernel_timing", "scpd_last_kernel_ms",
+           "scpd_kernel_name", "scpd_sigma", "scpd_channel_generate",
            "scpd_count_errors", "scpd_run_ber", "scpd_last_error", "scpd_status_string"]
 
 
@@ -187,6 +191,19 @@ class Decoder:
     @property
     def launches(self):
         return int(lib.scpd_launch_count(self._h))
+
+    @property
+    def kernel_name(self):
+        return lib.scpd_kernel_name(self._h).decode()
+
+    def kernel_timing(self, enable=True):
+        check(lib.scpd_kernel_timing(self._h, 1 if enable else 0))
+
+    def last_kernel_ms(self):
+        """Duration of the tree-walk kernel of the last decode (CUDA events on the decode's stream)."""
+        ms = ctypes.c_float()
+        check(lib.scpd_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def run_ber(self, ebn0_db, rate, nframes, first_frame=0, seed=0xF0, codeword=None):
         """src/testbench/main.cpp on the device: returns the six counters of scpd_run_ber."""

@@ -76,6 +76,7 @@ struct BsPlan {
 static inline int bs_planes(int q, int log2par, int ext, int l) {  // magnitude planes of alpha[l]
     return (q - 1) + ((ext && l < log2par) ? log2par - l : 0);
 }
+static inline size_t bs_planes_bytes(int q, int log2n) { return ((size_t)((q + 3) / 4) * 16u) << log2n; }  // per group
 static inline size_t bs_alpha_bytes(int q, int log2par, int ext, int l) {
     const int quads = (bs_planes(q, log2par, ext, l) + 1 + 3) / 4;
     return ((size_t)quads * 16u) << l;
@@ -93,7 +94,7 @@ static inline bool bs_make_plan(int log2n, int q, int log2par, int ext, size_t s
         return s;
     };
     auto b_bytes = [&](int lsb) { return std::min<size_t>((size_t)8u << lsb, 4 * n); };  // 2^(lsb+1) words
-    int lsa = log2n, lsb = log2n;
+    int lsa = log2n - 1, lsb = log2n;  // alpha[log2n] (the channel planes) has its own buffer
     while (a_total(lsa) + b_bytes(lsb) > smem_per_warp && (lsa > lmin || lsb > lmin)) {
         const size_t drop_a = lsa > lmin ? bs_alpha_bytes(q, log2par, ext, lsa) : 0;
         const size_t drop_b = lsb > lmin ? b_bytes(lsb) - b_bytes(lsb - 1) : 0;
@@ -102,7 +103,7 @@ static inline bool bs_make_plan(int log2n, int q, int log2par, int ext, size_t s
         else
             lsb--;
     }
-    if (force_lsa >= 0) lsa = std::min(log2n, std::max(lmin, force_lsa));
+    if (force_lsa >= 0) lsa = std::min(log2n - 1, std::max(lmin, force_lsa));
     if (force_lsb >= 0) lsb = std::min(log2n, std::max(lmin, force_lsb));
     if (a_total(lsa) + b_bytes(lsb) > smem_per_warp) return false;
     BsPlan p;
@@ -115,10 +116,11 @@ static inline bool bs_make_plan(int log2n, int q, int log2par, int ext, size_t s
     }
     p.sm_beta_off = (uint32_t)off;
     off += b_bytes(lsb);
+    off += 256;  // lanes past a small node read (never write) up to 4 * (32 + 31) bytes behind it
     p.sm_stride = (uint32_t)((off + 127) & ~(size_t)127);
     if (lanes_per_group < 32) p.sm_stride += 4u * (uint32_t)lanes_per_group;  // groups of a warp on distinct banks
     size_t woff = 0;
-    for (int l = lsa + 1; l <= log2n; l++) {
+    for (int l = lsa + 1; l < log2n; l++) {
         p.aoff[l] = (uint32_t)woff;
         woff += bs_alpha_bytes(q, log2par, ext, l);
     }

@@ -39,12 +39,22 @@
 #include "decode_fast.cuh"  // smem_u32 / lds128 / sts128 helpers
 #include "schedule.h"
 
+// register budget: CTAs of up to 128 threads, SCPD_BS_MINB of them per SM; SCPD_BS_U slots per lane and trip
+// in the generic-level loops
+#ifndef SCPD_BS_MINB
+#define SCPD_BS_MINB 4
+#endif
+#ifndef SCPD_BS_U
+#define SCPD_BS_U 4
+#endif
+
 namespace scpd {
 
 struct BsParams {
     const uint32_t* sched;  // bit-sliced op words (bs_plan.h: bs_compile_schedule)
     uint32_t sched_words;   // > 0: the CTA keeps a copy of the schedule behind the group regions in shared memory
-    const int8_t* llr;
+    const uint8_t* planes;  // alpha[log2n] of every group: (sign, |llr|) planes written by bs_planes_kernel
+    unsigned long long planes_stride;  // bytes per group
     uint32_t* xhat;
     unsigned long long nframes, ngroups;
     uint32_t n, log2n, wpf;
@@ -52,7 +62,7 @@ struct BsParams {
     uint32_t lsb;          // partial sums of nodes up to level lsb in shared memory (block of 2^(lsb+1) words)
     uint32_t sm_stride;    // bytes between the shared-memory regions of consecutive groups
     uint32_t sm_beta_off;  // byte offset of the partial-sum block inside a region
-    uint8_t* ws;           // workspace, per resident group: alpha levels > lsa, then n partial-sum words
+    uint8_t* ws;           // workspace, per resident group: alpha levels lsa < l < log2n, then n partial-sum words
     unsigned long long ws_stride;
     uint32_t ws_beta_off;
     uint32_t aoff[24];     // byte offset of alpha[l] inside the shared region (l <= lsa) or the workspace
@@ -72,8 +82,8 @@ static inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32
 static inline void sts32(uint32_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(smem_fast + a) = v; }
 #endif
 
-template <int FMT, int Q, int LOG2PAR, bool EXT, int G>
-__device__ __noinline__ void bs_sub2(uint32_t sm_lane, uint32_t sm_blane, int ll, uint32_t types, uint32_t ob);
+template <int FMT, int Q, int LOG2PAR, bool EXT, int G, int L>
+__device__ __noinline__ void bs_sub(uint32_t sm_lane, uint32_t sm_blane, int ll, uint32_t desc, uint32_t heap, uint32_t ob);
 
 // Node operations on the specialised levels (nodes of 2 .. 64 LLRs).  Everything lives in shared memory at
 // offsets that are compile-time constants; level, plane counts and trip counts are immediates.
@@ -154,8 +164,8 @@ struct BsLow {
         }
         __syncwarp();
     }
-    template <int L, bool ZERO>
-    __device__ __forceinline__ void g_low(uint32_t ob) {
+    template <int L>
+    __device__ __forceinline__ void g_low(uint32_t ob, bool zero) {  // zero: left child all-frozen, partial sums 0
         constexpr int P = plevel(L), PO = plevel(L - 1), H = 1 << (L - 1), IT = (H > G) ? H / G : 1, U = IT > 1 ? 2 : 1;
         const uint32_t src = sm_lane + aoff_low(L), dst = sm_lane + aoff_low(L - 1);
 #pragma unroll
@@ -167,7 +177,8 @@ struct BsLow {
             for (int u = 0; u < U; u++) {
                 load_sm<P, L>(src + 16u * ((it + u) * G), a[u]);
                 load_sm<P, L>(src + 16u * ((it + u) * G + H), b[u]);
-                u_[u] = ZERO ? 0u : lds32(sm_blane + ob + 4u * ((it + u) * G));
+                u_[u] = lds32(sm_blane + ob + 4u * ((it + u) * G));
+                if (zero) u_[u] = 0u;
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -182,13 +193,14 @@ struct BsLow {
         }
         __syncwarp();
     }
-    template <int L, bool COPY>
-    __device__ __forceinline__ void h_low(uint32_t ob) {
+    template <int L>
+    __device__ __forceinline__ void h_low(uint32_t ob, bool copy) {  // copy: left child all-frozen
         constexpr int H = 1 << (L - 1), IT = (H > G) ? H / G : 1;
 #pragma unroll
         for (int it = 0; it < IT; it++) {
             uint32_t x = lds32(sm_blane + ob + 4u * (H + it * G));
-            if (!COPY) x ^= lds32(sm_blane + ob + 4u * (it * G));
+            const uint32_t y = lds32(sm_blane + ob + 4u * (it * G));
+            if (!copy) x ^= y;
             if (H >= G || ll < H) sts32(sm_blane + ob + 4u * (it * G), x);
         }
         __syncwarp();
@@ -244,48 +256,45 @@ struct BsLow {
     // Fused walk of a subtree of 2^BS_LSUB LLRs: node types (2 bits per node, heap order) come from the
     // schedule, all branches are warp-uniform.  An all-information node whose LLRs contain a CA2 zero is
     // walked as a mixed node (its children are all-information again and take their own vote).
-    template <int L, int HEAP>
-    __device__ __forceinline__ void sub_node(uint32_t desc, uint32_t ob) {
-        const uint32_t t = (desc >> (2 * HEAP)) & 3u;
-        if constexpr (L == 1) {
-            p2_low(t, ob);
-        } else if constexpr (L == 2 && HEAP != 0) {
-            // one out-of-line copy of the 4-LLR node keeps the fused routine inside the instruction cache
-            const uint32_t tl = (desc >> (2 * (2 * HEAP + 1))) & 3u, tr = (desc >> (2 * (2 * HEAP + 2))) & 3u;
-            bs_sub2<FMT, Q, LOG2PAR, EXT, G>(sm_lane, sm_blane, ll, t | (tl << 2) | (tr << 4), ob);
-        } else {
-            constexpr int H = 1 << (L - 1);
-            if (t == T_R0) return this->template r0_low<L>(ob);
-            if (t == T_R1) {
-                if (!r1_low<L>(ob)) return;
-            }
-            const uint32_t tl = (desc >> (2 * (2 * HEAP + 1))) & 3u, tr = (desc >> (2 * (2 * HEAP + 2))) & 3u;
-            if (tl == T_R0) {
-                this->template g_low<L, true>(ob);
-                sub_node<L - 1, 2 * HEAP + 2>(desc, ob + 4u * H);
-                return this->template h_low<L, true>(ob);
-            }
-            this->template f_low<L>();
-            sub_node<L - 1, 2 * HEAP + 1>(desc, ob);
-            if (tr == T_R0) {
-                r0_low<L - 1>(ob + 4u * H);
-            } else {
-                this->template g_low<L, false>(ob);
-                sub_node<L - 1, 2 * HEAP + 2>(desc, ob + 4u * H);
-            }
-            this->template h_low<L, false>(ob);
+    // `types`: this node, left child, right child (2 bits each) for the out-of-line levels; `desc`: the whole subtree.
+    template <int L>
+    __device__ __forceinline__ void sub_body(uint32_t desc, uint32_t heap, uint32_t ob) {
+        constexpr int H = 1 << (L - 1);
+        const uint32_t t = (desc >> (2 * heap)) & 3u;
+        if (t == T_R0) return r0_low<L>(ob);
+        if (t == T_R1) {
+            if (!r1_low<L>(ob)) return;
         }
+        const uint32_t tl = (desc >> (2 * (2 * heap + 1))) & 3u, tr = (desc >> (2 * (2 * heap + 2))) & 3u;
+        const bool left0 = tl == T_R0;
+        if (!left0) {
+            f_low<L>();
+            sub_child<L - 1>(desc, 2 * heap + 1, ob);
+        }
+        if (tr == T_R0) {
+            r0_low<L - 1>(ob + 4u * H);
+        } else {
+            g_low<L>(ob, left0);
+            sub_child<L - 1>(desc, 2 * heap + 2, ob + 4u * H);
+        }
+        h_low<L>(ob, left0);
     }
-
+    template <int L>
+    __device__ __forceinline__ void sub_child(uint32_t desc, uint32_t heap, uint32_t ob) {
+        if constexpr (L == 1)
+            p2_low((desc >> (2 * heap)) & 3u, ob);
+        else  // one out-of-line copy per level keeps the fused routine inside the instruction cache
+            bs_sub<FMT, Q, LOG2PAR, EXT, G, L>(sm_lane, sm_blane, ll, desc, heap, ob);
+    }
 };
 
-template <int FMT, int Q, int LOG2PAR, bool EXT, int G>
-__device__ __noinline__ void bs_sub2(uint32_t sm_lane, uint32_t sm_blane, int ll, uint32_t types, uint32_t ob) {
+template <int FMT, int Q, int LOG2PAR, bool EXT, int G, int L>
+__device__ __noinline__ void bs_sub(uint32_t sm_lane, uint32_t sm_blane, int ll, uint32_t desc, uint32_t heap, uint32_t ob) {
     BsLow<FMT, Q, LOG2PAR, EXT, G> low;
     low.ll = ll;
     low.sm_lane = sm_lane;
     low.sm_blane = sm_blane;
-    low.template sub_node<2, 0>(types, ob);  // local heap: node 0, terminals 1 and 2
+    low.template sub_body<L>(desc, heap, ob);
 }
 
 template <int FMT, int Q, int LOG2PAR, bool EXT, int G>
@@ -306,6 +315,7 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
     uint8_t* smp_grp;   // ... to this lane's group region
     uint8_t* ws_warp;
     uint8_t* ws_grp;
+    const uint8_t* pl_grp;  // channel planes of the group being decoded
     uint32_t bmask;     // byte mask of the shared partial-sum block
     uint32_t sm_sched;  // shared-window byte address of the schedule copy
 
@@ -314,7 +324,8 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
     // ------------------------------------------------------------ storage of the generic levels
     // One code path for shared memory and workspace: arrays are reached through generic pointers (the
     // instruction-cache footprint of per-space variants cost more than the generic loads do).
-    __device__ __forceinline__ uint8_t* aptr(int l) const {  // alpha[l]
+    __device__ __forceinline__ uint8_t* aptr(int l) const {  // alpha[l]; the channel level is only read
+        if ((uint32_t)l == p.log2n) return const_cast<uint8_t*>(pl_grp);
         return ((uint32_t)l <= p.lsa ? smp_grp : ws_grp) + p.aoff[l];
     }
     __device__ __forceinline__ uint8_t* bptr(int l, uint32_t o) const {  // partial sums of node (l, o)
@@ -340,39 +351,10 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
 #pragma unroll
         for (int k = 1; k < 4 * NVQ; k++) w[k] = (k <= PQ) ? x.m[k - 1] : 0u;
 #pragma unroll
-        for (int v = 0; v < NVQ; v++)
+        for (int v = 0; v < NVQ; v++) {
             *reinterpret_cast<uint4*>(base + (((size_t)v << l) + i) * 16u) =
                 make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-    }
-
-    // ------------------------------------------------------------ channel rows -> planes
-    // alpha[log2n] := (sign, |llr|) planes of the 32 frames of a group; the whole warp works on one
-    // group at a time, lane L transposing the four LLRs 128c + 4L .. +3 of every frame.   wrapper_in.h:30-42
-    __device__ __forceinline__ void load_channel(unsigned long long g0) {
-        const bool dsm = p.log2n <= p.lsa;
-        for (int s = 0; s < GPW; s++) {
-            const unsigned long long f0 = (g0 + s) * 32ull;
-            const uint32_t nvalid = f0 >= p.nframes ? 0u : (p.nframes - f0 < 32ull ? (uint32_t)(p.nframes - f0) : 32u);
-            uint8_t* dst = (dsm ? smp_warp + (size_t)s * p.sm_stride : ws_warp + (unsigned long long)s * p.ws_stride) +
-                           p.aoff[p.log2n];
-            const int8_t* row0 = p.llr + f0 * p.n + 4u * lane;
-            for (uint32_t c = 0; c < p.n; c += 128u) {
-                uint32_t a[32];
-#pragma unroll
-                for (int f = 0; f < 32; f++)
-                    a[f] = ((uint32_t)f < nvalid) ? __ldg(reinterpret_cast<const uint32_t*>(row0 + (size_t)f * p.n + c)) : 0u;
-                bs::transpose32(a);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t v[8] = {a[8 * k], a[8 * k + 1], a[8 * k + 2], a[8 * k + 3],
-                                           a[8 * k + 4], a[8 * k + 5], a[8 * k + 6], a[8 * k + 7]};
-                    bs::Val<PQ> x;
-                    bs::from_int8_planes<PQ>(v, x);
-                    store(dst, (int)p.log2n, c + 4u * lane + k, x);
-                }
-            }
         }
-        __syncwarp();
     }
 
     // ------------------------------------------------------------ generic levels (nodes of 128 LLRs and more)
@@ -392,7 +374,7 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
         for (int u = 0; u < U; u++) store(dst, l - 1, i + u * G, r[u]);
     }
     __device__ __forceinline__ void op_f(int l) {
-        constexpr int U = 4;
+        constexpr int U = SCPD_BS_U;
         const uint32_t h = 1u << (l - 1);
         const uint8_t* src = aptr(l);
         uint8_t* dst = aptr(l - 1);
@@ -420,7 +402,7 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
         for (int u = 0; u < U; u++) store(dst, l - 1, i + u * G, r[u]);
     }
     __device__ __forceinline__ void op_g(int l, uint32_t o, bool zero) {
-        constexpr int U = 4;
+        constexpr int U = SCPD_BS_U;
         const uint32_t h = 1u << (l - 1);
         const uint8_t* src = aptr(l);
         uint8_t* dst = aptr(l - 1);
@@ -454,7 +436,9 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
     }
     __device__ __forceinline__ void op_r0(int l, uint32_t o) {
         uint8_t* d = bptr(l, o);
-        for (uint32_t i = 4u * ll; i < (1u << l); i += 4u * G) *reinterpret_cast<uint4*>(d + 4u * i) = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = 4u * ll; i < (1u << l); i += 4u * G) {
+            *reinterpret_cast<uint4*>(d + 4u * i) = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncwarp();
     }
     // hard decision of node (l,o); returns true (warp-uniform) if some LLR of some frame is a CA2 zero
@@ -479,16 +463,14 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
         return any;
     }
 
-    template <bool SSM>
     __device__ __forceinline__ uint32_t fetch(uint32_t pc) const {
-        return SSM ? lds32(sm_sched + 4u * pc) : __ldg(p.sched + pc);
+        return p.sched_words ? lds32(sm_sched + 4u * pc) : __ldg(p.sched + pc);
     }
-    template <bool SSM>
     __device__ __forceinline__ void run() {
         uint32_t pc = 0;
-        uint32_t w = fetch<SSM>(pc);
+        uint32_t w = fetch(pc);
         for (;;) {
-            const uint32_t wn = fetch<SSM>(pc + 1);  // the next word: an op, node types, or a skip count
+            const uint32_t wn = fetch(pc + 1);  // the next word: an op, node types, or a skip count
             // Ops outside every rate-1 fallback region are executed by all warps of the CTA: meeting there
             // keeps the warps in the same stretch of code (one instruction-cache fill serves all of them).
             if (bs_op_sync(w)) __syncthreads();
@@ -499,7 +481,7 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
             uint32_t adv = 1;
             bool z;
             if (code == 8 * BS_LSUB + BSK_F) {  // by far the most frequent op
-                this->template sub_node<BS_LSUB, 0>(wn, ob);
+                this->template sub_body<BS_LSUB>(wn, 0u, ob);
                 adv = 2;
             } else {
                 switch (code) {
@@ -507,10 +489,10 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
                     case 8 * BS_LSUB + BSK_R0: this->template r0_low<BS_LSUB>(ob); break;
 #define BS_LOW(L)                                                           \
     case 8 * L + BSK_F: this->template f_low<L>(); break;                  \
-    case 8 * L + BSK_G: this->template g_low<L, false>(ob); break;         \
-    case 8 * L + BSK_G0: this->template g_low<L, true>(ob); break;         \
-    case 8 * L + BSK_H: this->template h_low<L, false>(ob); break;         \
-    case 8 * L + BSK_HCOPY: this->template h_low<L, true>(ob); break;      \
+    case 8 * L + BSK_G:                                                     \
+    case 8 * L + BSK_G0: this->template g_low<L>(ob, code == 8 * L + BSK_G0); break;   \
+    case 8 * L + BSK_H:                                                     \
+    case 8 * L + BSK_HCOPY: this->template h_low<L>(ob, code == 8 * L + BSK_HCOPY); break; \
     case 8 * L + BSK_R0: this->template r0_low<L>(ob); break;              \
     case 8 * L + BSK_R1:                                                    \
         z = this->template r1_low<L>(ob);                                  \
@@ -520,10 +502,10 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
                     BS_LOW(5) BS_LOW(6)
 #undef BS_LOW
                     case 8 * (BS_LLOW + 1) + BSK_F: op_f(l); break;
-                    case 8 * (BS_LLOW + 1) + BSK_G: op_g(l, o, false); break;
-                    case 8 * (BS_LLOW + 1) + BSK_G0: op_g(l, o, true); break;
-                    case 8 * (BS_LLOW + 1) + BSK_H: op_h(l, o, false); break;
-                    case 8 * (BS_LLOW + 1) + BSK_HCOPY: op_h(l, o, true); break;
+                    case 8 * (BS_LLOW + 1) + BSK_G:
+                    case 8 * (BS_LLOW + 1) + BSK_G0: op_g(l, o, code == 8 * (BS_LLOW + 1) + BSK_G0); break;
+                    case 8 * (BS_LLOW + 1) + BSK_H:
+                    case 8 * (BS_LLOW + 1) + BSK_HCOPY: op_h(l, o, code == 8 * (BS_LLOW + 1) + BSK_HCOPY); break;
                     case 8 * (BS_LLOW + 1) + BSK_R0: op_r0(l, o); break;
                     case 8 * (BS_LLOW + 1) + BSK_R1:  // hard decision; the plain-SC ops behind it run only on a CA2 zero
                         z = op_hd(l, o);
@@ -534,7 +516,7 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
                 }
             }
             pc += adv;
-            w = (adv == 1) ? wn : fetch<SSM>(pc);
+            w = (adv == 1) ? wn : fetch(pc);
         }
     }
 
@@ -567,19 +549,62 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
     }
     // g0: first of the GPW groups this warp decodes together
     __device__ __forceinline__ void decode_groups(unsigned long long g0) {
-        load_channel(g0);
-        if (p.sched_words)
-            run<true>();
-        else
-            run<false>();
+        // lane groups past the end of the batch decode the last group again and write nothing
+        const unsigned long long g = g0 + (unsigned long long)(lane / G);
+        pl_grp = p.planes + (g < p.ngroups ? g : p.ngroups - 1) * p.planes_stride;
+        run();
         write_output(g0);
     }
 };
 
+// int8 rows -> bit planes: alpha[log2n] of every group, (sign, |llr|) in the plane-quad layout of the decode
+// kernel (quad v of LLR i at byte ((v << log2n) + i) * 16).  One warp per (group, 128 LLRs): lane L reads the
+// four LLRs 128c + 4L .. +3 of each of the 32 frames (coalesced 128-byte row segments), transposes the
+// 32 x 32 bit matrix in registers and converts two's complement to sign-magnitude.      wrapper_in.h:30-42
+template <int Q>
+__global__ void __launch_bounds__(256) bs_planes_kernel(const int8_t* __restrict__ llr, unsigned long long nframes,
+                                                        uint32_t n, uint32_t log2n, uint8_t* __restrict__ planes,
+                                                        unsigned long long planes_stride) {
+    constexpr int PQ = Q - 1, NVQ = (Q + 3) / 4;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long chunks = n / 128u, ngroups = (nframes + 31) / 32;
+    const unsigned long long ntasks = ngroups * chunks;
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntasks; t += wstride) {
+        const unsigned long long g = t / chunks;
+        const uint32_t c = (uint32_t)(t % chunks) * 128u;
+        const unsigned long long f0 = g * 32ull;
+        const uint32_t nvalid = nframes - f0 < 32ull ? (uint32_t)(nframes - f0) : 32u;
+        const int8_t* row0 = llr + f0 * n + c + 4u * lane;
+        uint32_t a[32];
+#pragma unroll
+        for (int f = 0; f < 32; f++)
+            a[f] = ((uint32_t)f < nvalid) ? __ldg(reinterpret_cast<const uint32_t*>(row0 + (size_t)f * n)) : 0u;
+        bs::transpose32(a);
+        uint8_t* dst = planes + g * planes_stride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v[8] = {a[8 * k], a[8 * k + 1], a[8 * k + 2], a[8 * k + 3],
+                                   a[8 * k + 4], a[8 * k + 5], a[8 * k + 6], a[8 * k + 7]};
+            bs::Val<PQ> x;
+            bs::from_int8_planes<PQ>(v, x);
+            uint32_t w[4 * NVQ];
+            w[0] = x.s;
+#pragma unroll
+            for (int j = 1; j < 4 * NVQ; j++) w[j] = (j <= PQ) ? x.m[j - 1] : 0u;
+            const uint32_t i = c + 4u * lane + k;
+#pragma unroll
+            for (int q = 0; q < NVQ; q++)
+                *reinterpret_cast<uint4*>(dst + (((size_t)q << log2n) + i) * 16u) =
+                    make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
+    }
+}
+
 // Every warp of a CTA walks the same schedule the same number of times (the barriers in run() rely on it);
 // warps or lane groups without frames decode zeros and write nothing.
 template <int FMT, int Q, int LOG2PAR, bool EXT, int G>
-__global__ void __launch_bounds__(512) sc_decode_bs_kernel(const BsParams p) {
+__global__ void __launch_bounds__(128, SCPD_BS_MINB) sc_decode_bs_kernel(const BsParams p) {
     extern __shared__ __align__(16) uint8_t smem_fast[];
     constexpr int GPW = 32 / G;
     const int warp = threadIdx.x >> 5;

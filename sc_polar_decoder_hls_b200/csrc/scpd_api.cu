@@ -137,6 +137,17 @@ struct scpd_decoder {
     size_t bs_smem_bytes = 0;
     uint8_t* d_bs_ws = nullptr;
     size_t bs_ws_bytes = 0;
+    uint8_t* d_bs_planes = nullptr;
+    size_t bs_planes_bytes = 0;
+    // timing of the dominant kernel (scpd_kernel_timing)
+    bool timing = false;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    // pipeline of scpd_decode_host: copy-in, compute and copy-out streams over double-buffered staging
+    cudaStream_t st_in = nullptr, st_comp = nullptr, st_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_dec[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int8_t* d_llr2[2] = {nullptr, nullptr};
+    uint32_t* d_xhat2[2] = {nullptr, nullptr};
+    size_t pipe_frames = 0;
     // staging for scpd_decode_host / scpd_run_ber
     int8_t* d_llr = nullptr;
     uint32_t* d_xhat = nullptr;
@@ -184,15 +195,28 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
 #define BS_K(F, Q, LP, E, GG)                                                                  \
     if (fmt == F && q == Q && log2par == LP && ext == (E ? 1 : 0) && (g == GG || g == 0)) \
         return sc_decode_bs_kernel<F, Q, LP, E, GG>;
-    BS_K(0, 8, 4, true, 8)
-    BS_K(0, 8, 4, true, 16)
+    // the BASELINE setting (CA2, Q = 8, PAR = 16, EXTENDED) in every group width
     BS_K(0, 8, 4, true, 32)
+    BS_K(0, 8, 4, true, 16)
+    BS_K(0, 8, 4, true, 8)
 #ifndef SCPD_FAST_BUILD
-    BS_K(0, 8, 4, false, 8)
-    BS_K(0, 6, 4, true, 8)
-    BS_K(1, 6, 4, true, 8)
-    BS_K(1, 6, 4, false, 8)
-    BS_K(1, 8, 4, true, 8)
+    // CA2: other quantisations / leaf widths of script/script_tests.sh
+    BS_K(0, 8, 4, false, 32)
+    BS_K(0, 7, 4, true, 32)
+    BS_K(0, 6, 4, true, 32)
+    BS_K(0, 6, 4, false, 32)
+    BS_K(0, 8, 2, true, 32)
+    BS_K(0, 8, 6, true, 32)
+    BS_K(0, 7, 1, true, 32)
+    // SIGMAG (the reference's checked-in default is SIGMAG, LLR_BITS 6: config.h:2,11)
+    BS_K(1, 6, 4, true, 32)
+    BS_K(1, 6, 4, false, 32)
+    BS_K(1, 6, 6, true, 32)
+    BS_K(1, 7, 6, true, 32)
+    BS_K(1, 8, 4, true, 32)
+    BS_K(1, 8, 4, false, 32)
+#else
+    BS_K(1, 6, 4, true, 32)
 #endif
 #undef BS_K
     return nullptr;
@@ -201,25 +225,28 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
 // Decide whether the bit-sliced kernel applies and lay out its shared memory / workspace.
 static int plan_bs(scpd_decoder* d, const uint8_t* flags) {
     d->bs_ok = false;
+    // SCPD_KERNEL = bs | fast | generic pins the kernel family (tests, profiling); default: the first that applies
     const char* ksel = std::getenv("SCPD_KERNEL");
-    if (ksel && std::strcmp(ksel, "bs") != 0 && d->cfg.format == SCPD_FMT_CA2) return SCPD_OK;
-    int g = env_int("SCPD_BS_GROUP", 8);
+    if (ksel && std::strcmp(ksel, "bs") != 0 && std::strcmp(ksel, "auto") != 0 && d->cfg.format == SCPD_FMT_CA2)
+        return SCPD_OK;
+    // lanes per frame group: narrow groups pay off while the tree is small (measured: profiles/README.md)
+    int g = env_int("SCPD_BS_GROUP", d->log2n <= 11 ? 16 : 32);
     bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, g);
     if (!k) {
-        g = 8;
+        g = 32;
         k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, g);
     }
     if (!k || d->log2n < 7) return SCPD_OK;
     d->bs_group = g;
-    d->bs_warps = std::max(1, std::min(16, env_int("SCPD_BS_WARPS", 8)));
-    const size_t per_group = (size_t)env_int("SCPD_BS_SMEM_KB", 13) * 1024;
+    d->bs_warps = std::max(1, std::min(4, env_int("SCPD_BS_WARPS", 4)));
+    const size_t per_group = (size_t)env_int("SCPD_BS_SMEM_KB", 7) * 1024;
     if (!bs_make_plan(d->log2n, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, per_group, &d->bs_plan,
                       env_int("SCPD_BS_LSA", -1), env_int("SCPD_BS_LSB", -1), g))
         return SCPD_OK;
     {
         const std::vector<uint32_t> ops = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning,
                                                          flags, &d->bs_stats, BS_LSUB, d->cfg.format == SCPD_FMT_CA2 ? 1 : 2);
-        if (!bs_compile_schedule(ops, &d->bs_sched_host, env_int("SCPD_BS_SYNC", 1))) return SCPD_OK;
+        if (!bs_compile_schedule(ops, &d->bs_sched_host, env_int("SCPD_BS_SYNC", 0))) return SCPD_OK;
     }
     // a schedule of up to 8 KB is copied into shared memory by every CTA (op fetches then never miss)
     d->bs_sched_smem = d->bs_sched_host.size() <= (size_t)env_int("SCPD_BS_SCHED_SMEM_WORDS", 2048);
@@ -431,6 +458,19 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_fast_ws);
     cudaFree(d->d_bs_sched);
     cudaFree(d->d_bs_ws);
+    cudaFree(d->d_bs_planes);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(d->d_llr2[b]);
+        cudaFree(d->d_xhat2[b]);
+        if (d->ev_in[b]) cudaEventDestroy(d->ev_in[b]);
+        if (d->ev_dec[b]) cudaEventDestroy(d->ev_dec[b]);
+        if (d->ev_out[b]) cudaEventDestroy(d->ev_out[b]);
+    }
+    if (d->ev_k0) cudaEventDestroy(d->ev_k0);
+    if (d->ev_k1) cudaEventDestroy(d->ev_k1);
+    if (d->st_in) cudaStreamDestroy(d->st_in);
+    if (d->st_comp) cudaStreamDestroy(d->st_comp);
+    if (d->st_out) cudaStreamDestroy(d->st_out);
     cudaFree(d->d_llr);
     cudaFree(d->d_xhat);
     cudaFree(d->d_counters);
@@ -470,7 +510,9 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     p.ws = d->d_fast_ws;
     p.ws_stride = d->fast_ws_stride;
     fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(d->fast_warps * 32)), d->fast_smem_bytes, st>>>(p);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
@@ -491,10 +533,32 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
         CUDA_TRY(cudaMalloc(&d->d_bs_ws, ws_need));
         d->bs_ws_bytes = ws_need;
     }
+    const size_t pl_stride = bs_planes_bytes((int)d->cfg.llr_bits, d->log2n);
+    const size_t pl_need = (size_t)ngroups * pl_stride;
+    if (pl_need > d->bs_planes_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_bs_planes);
+        d->d_bs_planes = nullptr;
+        d->bs_planes_bytes = 0;
+        CUDA_TRY(cudaMalloc(&d->d_bs_planes, pl_need));
+        d->bs_planes_bytes = pl_need;
+    }
+    {   // int8 rows -> bit planes, one warp per (group, 128 LLRs)
+        const unsigned long long tasks = ngroups * (d->cfg.n / 128u);
+        const unsigned blocks = (unsigned)std::min<unsigned long long>((tasks + 7) / 8, (unsigned long long)d->num_sms * 32);
+        switch (d->cfg.llr_bits) {
+            case 6: bs_planes_kernel<6><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, (uint32_t)d->log2n, d->d_bs_planes, pl_stride); break;
+            case 7: bs_planes_kernel<7><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, (uint32_t)d->log2n, d->d_bs_planes, pl_stride); break;
+            default: bs_planes_kernel<8><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, (uint32_t)d->log2n, d->d_bs_planes, pl_stride); break;
+        }
+        d->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     BsParams p;
     p.sched = d->d_bs_sched;
     p.sched_words = d->bs_sched_smem ? (uint32_t)d->bs_sched_host.size() : 0u;
-    p.llr = d_llr;
+    p.planes = d->d_bs_planes;
+    p.planes_stride = pl_stride;
     p.xhat = d_xhat;
     p.nframes = nframes;
     p.ngroups = ngroups;
@@ -510,7 +574,9 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.ws_beta_off = d->bs_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->bs_plan.aoff[l];
     bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->bs_group);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(d->bs_warps * 32)), d->bs_smem_bytes, st>>>(p);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
@@ -559,11 +625,13 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     p.ws = d->d_ws;
     p.ws_words_per_fp = d->ws_words_per_fp;
     const dim3 g((unsigned)grid), b((unsigned)(d->warps_per_cta * 32));
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     switch (d->group) {
         case 8: sc_decode_generic_kernel<8><<<g, b, d->smem_bytes, st>>>(p); break;
         case 16: sc_decode_generic_kernel<16><<<g, b, d->smem_bytes, st>>>(p); break;
         default: sc_decode_generic_kernel<32><<<g, b, d->smem_bytes, st>>>(p); break;
     }
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
@@ -582,19 +650,99 @@ static int ensure_stage(scpd_decoder* d, size_t nframes) {
     return SCPD_OK;
 }
 
+static int ensure_pipeline(scpd_decoder* d, size_t chunk) {
+    if (!d->st_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->st_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->st_comp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->st_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_in[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_dec[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    if (chunk <= d->pipe_frames) return SCPD_OK;
+    for (int b = 0; b < 2; b++) {
+        cudaFree(d->d_llr2[b]);
+        cudaFree(d->d_xhat2[b]);
+        d->d_llr2[b] = nullptr;
+        d->d_xhat2[b] = nullptr;
+    }
+    d->pipe_frames = 0;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&d->d_llr2[b], chunk * (size_t)d->cfg.n));
+        CUDA_TRY(cudaMalloc(&d->d_xhat2[b], chunk * (size_t)d->wpf * 4));
+    }
+    d->pipe_frames = chunk;
+    return SCPD_OK;
+}
+
+// Host-buffer entry point.  The batch is cut into chunks (about 256 MiB of LLRs each) that flow through a
+// three-stage pipeline -- H2D copy, decode, D2H copy, one stream each, double-buffered staging -- so that
+// the PCIe transfers of neighbouring chunks overlap the decode and each other (full duplex).
 extern "C" int scpd_decode_host(scpd_decoder* d, const int8_t* h_llr, size_t nframes, uint32_t* h_xhat) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_decode_host: null decoder");
     if (nframes == 0) return SCPD_OK;
     if (!h_llr || !h_xhat) return set_error(SCPD_E_ARG, "scpd_decode_host: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
-    int rc = ensure_stage(d, nframes);
+    const size_t n = d->cfg.n, row_out = (size_t)d->wpf * 4;
+    size_t chunk = ((size_t)env_int("SCPD_HOST_CHUNK_MB", 256) << 20) / n;
+    chunk = std::max<size_t>(32, chunk & ~(size_t)31);
+    if (chunk > nframes) chunk = nframes;
+    int rc = ensure_pipeline(d, chunk);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d->d_llr, h_llr, nframes * (size_t)d->cfg.n, cudaMemcpyHostToDevice, 0));
-    rc = scpd_decode(d, d->d_llr, nframes, d->d_xhat, 0);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h_xhat, d->d_xhat, nframes * (size_t)d->wpf * 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    size_t i = 0;
+    for (size_t f0 = 0; f0 < nframes; f0 += chunk, i++) {
+        const int b = (int)(i & 1);
+        const size_t nb = std::min(chunk, nframes - f0);
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(d->st_in, d->ev_dec[b], 0));  // decode i-2 has consumed this buffer
+        CUDA_TRY(cudaMemcpyAsync(d->d_llr2[b], h_llr + f0 * n, nb * n, cudaMemcpyHostToDevice, d->st_in));
+        CUDA_TRY(cudaEventRecord(d->ev_in[b], d->st_in));
+        CUDA_TRY(cudaStreamWaitEvent(d->st_comp, d->ev_in[b], 0));
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(d->st_comp, d->ev_out[b], 0));  // copy-out i-2 has drained this buffer
+        rc = scpd_decode(d, d->d_llr2[b], nb, d->d_xhat2[b], d->st_comp);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(d->ev_dec[b], d->st_comp));
+        CUDA_TRY(cudaStreamWaitEvent(d->st_out, d->ev_dec[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h_xhat) + f0 * row_out, d->d_xhat2[b], nb * row_out,
+                                 cudaMemcpyDeviceToHost, d->st_out));
+        CUDA_TRY(cudaEventRecord(d->ev_out[b], d->st_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(d->st_out));
+    CUDA_TRY(cudaStreamSynchronize(d->st_comp));
+    CUDA_TRY(cudaStreamSynchronize(d->st_in));
     return SCPD_OK;
+}
+
+extern "C" int scpd_kernel_timing(scpd_decoder* d, int enable) {
+    if (!d) return set_error(SCPD_E_ARG, "scpd_kernel_timing: null decoder");
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (enable && !d->ev_k0) {
+        CUDA_TRY(cudaEventCreate(&d->ev_k0));
+        CUDA_TRY(cudaEventCreate(&d->ev_k1));
+    }
+    d->timing = enable != 0;
+    return SCPD_OK;
+}
+extern "C" int scpd_last_kernel_ms(scpd_decoder* d, float* ms) {
+    if (!d || !ms) return set_error(SCPD_E_ARG, "scpd_last_kernel_ms: null argument");
+    if (!d->timing || !d->ev_k1) return set_error(SCPD_E_ARG, "scpd_last_kernel_ms: timing is off");
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaEventSynchronize(d->ev_k1));
+    CUDA_TRY(cudaEventElapsedTime(ms, d->ev_k0, d->ev_k1));
+    return SCPD_OK;
+}
+extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
+    static thread_local char buf[96];
+    if (!d) return "";
+    if (d->bs_ok)
+        snprintf(buf, sizeof buf, "sc_decode_bs_kernel (bit-sliced, %d lanes per 32-frame group, %d warps/CTA)", d->bs_group,
+                 d->bs_warps);
+    else if (d->fast_group)
+        snprintf(buf, sizeof buf, "sc_decode_fast_kernel (int16x2, %d lanes per frame pair)", d->fast_group);
+    else
+        snprintf(buf, sizeof buf, "sc_decode_generic_kernel (int16x2, %d lanes per frame pair)", d->group);
+    return buf;
 }
 
 extern "C" int scpd_extract_info(scpd_decoder* d, const uint32_t* d_xhat, size_t nframes, uint32_t* d_uhat,

@@ -215,13 +215,41 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
     BsParams& p = L.p;
     p.sched = sched.data();
     p.sched_words = 0;  // the emulator runs the warps of a CTA one after the other: no __syncthreads
-    p.llr = llr;
     p.xhat = xhat;
     p.nframes = nframes;
     p.ngroups = (nframes + 31) / 32;
     p.n = 1u << log2n;
     p.log2n = (uint32_t)log2n;
     p.wpf = p.n / 32;
+    // channel planes: the transposing kernel, one emulated warp per CTA
+    const size_t pl_stride = bs_planes_bytes(llr_bits, log2n);
+    std::vector<uint8_t> planes((size_t)p.ngroups * pl_stride + 256, 0xAB);
+    uint8_t* pl = reinterpret_cast<uint8_t*>(((uintptr_t)planes.data() + 255) & ~(uintptr_t)255);
+    {
+        struct PL {
+            const int8_t* llr;
+            unsigned long long nframes;
+            uint32_t n, log2n;
+            uint8_t* planes;
+            unsigned long long stride;
+            int q;
+        } P{llr, nframes, p.n, (uint32_t)log2n, pl, pl_stride, llr_bits};
+        void (*pbody)(void*) = [](void* a) {
+            PL* x = static_cast<PL*>(a);
+            if (x->q == 6) bs_planes_kernel<6>(x->llr, x->nframes, x->n, x->log2n, x->planes, x->stride);
+            else if (x->q == 7) bs_planes_kernel<7>(x->llr, x->nframes, x->n, x->log2n, x->planes, x->stride);
+            else bs_planes_kernel<8>(x->llr, x->nframes, x->n, x->log2n, x->planes, x->stride);
+        };
+        dim3 pg, pb, pi;
+        pg.x = 3;
+        pb.x = 32;
+        for (unsigned b = 0; b < pg.x; b++) {
+            pi.x = b;
+            cuda_emu::run_warp(pbody, &P, pi, pg, pb, 0);
+        }
+    }
+    p.planes = pl;
+    p.planes_stride = pl_stride;
     p.lsa = plan.lsa;
     p.lsb = plan.lsb;
     p.sm_stride = plan.sm_stride;

@@ -27,13 +27,13 @@ def scpd():
 _ORACLE_CACHE = {}
 
 
-def _oracle(n, par, q, ext, flags, llr):
+def _oracle(n, par, q, ext, flags, llr, fmt=0):
     """Oracle output is independent of pruning mode and kernel variant: compute once per input."""
-    key = (n, par, q, ext, flags.tobytes(), llr.shape, hash(llr.tobytes()))
+    key = (n, par, q, ext, fmt, flags.tobytes(), llr.shape, hash(llr.tobytes()))
     if key not in _ORACLE_CACHE:
         if len(_ORACLE_CACHE) > 64:
             _ORACLE_CACHE.clear()
-        _ORACLE_CACHE[key] = ol.decode_packed(n, par, q, 0, ext, flags, llr, threads=8)
+        _ORACLE_CACHE[key] = ol.decode_packed(n, par, q, fmt, ext, flags, llr, threads=8)
     return _ORACLE_CACHE[key]
 
 
@@ -47,32 +47,43 @@ def _llrs(seed, n, nfr, k, snr):
     return _LLR_CACHE[key]
 
 
-def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device"):
+def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
     import torch
     flags = scpd.packed_flags(name, n)
-    dec = scpd.Decoder(n, k, flags, par=par, llr_bits=q, fmt=scpd.FMT_CA2, extended=ext, pruning=prune)
+    dec = scpd.Decoder(n, k, flags, par=par, llr_bits=q, fmt=fmt, extended=ext, pruning=prune)
     if via == "host":
         got = dec.decode_host(llr)
     else:
         x = dec.decode(torch.from_numpy(llr).cuda())
         torch.cuda.synchronize()
         got = x.cpu().numpy().view(np.uint32)
-    want = _oracle(n, par, q, ext, flags, llr)
+    want = _oracle(n, par, q, ext, flags, llr, fmt)
     bad = np.nonzero((got != want).any(axis=1))[0]
-    assert bad.size == 0, f"{bad.size} of {len(llr)} frames differ (first {bad[:5]}) {name} par={par} q={q} ext={ext} prune={prune}"
+    assert bad.size == 0, (f"{bad.size} of {len(llr)} frames differ (first {bad[:5]}) {name} par={par} q={q} ext={ext} "
+                           f"prune={prune} fmt={fmt}")
     dec.close()
 
 
-@pytest.fixture(params=["auto", "generic", "fast2", "fast4", "fast16"])
+@pytest.fixture(params=["auto", "generic", "fast2", "fast8", "fast16", "bs8", "bs16", "bs32", "bs32ws"])
 def kernel_mode(request, monkeypatch):
-    """Selects the decode kernel through the library's environment switches (read in scpd_create)."""
+    """Selects the decode kernel through the library's environment switches (read in scpd_create):
+    the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
+    workspace early, one warp per CTA), the int16x2 kernel with 2 / 8 / 16 lanes per frame pair, the
+    generic kernel, and the library's own choice."""
     mode = request.param
-    monkeypatch.delenv("SCPD_KERNEL", raising=False)
-    monkeypatch.delenv("SCPD_GROUP", raising=False)
+    for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS"):
+        monkeypatch.delenv(v, raising=False)
     if mode == "generic":
         monkeypatch.setenv("SCPD_KERNEL", "generic")
     elif mode.startswith("fast"):
+        monkeypatch.setenv("SCPD_KERNEL", "fast")
         monkeypatch.setenv("SCPD_GROUP", mode[4:])
+    elif mode.startswith("bs"):
+        monkeypatch.setenv("SCPD_KERNEL", "bs")
+        monkeypatch.setenv("SCPD_BS_GROUP", mode[2:4].rstrip("w"))
+        if mode.endswith("ws"):
+            monkeypatch.setenv("SCPD_BS_LSB", "6")
+            monkeypatch.setenv("SCPD_BS_WARPS", "1")
     return mode
 
 
@@ -104,11 +115,40 @@ def test_golden_codewords_noiseless(scpd):
 
 @pytest.mark.parametrize("prune", [0, 1, 2])
 @pytest.mark.parametrize("par,q,ext", [(16, 8, 1), (16, 8, 0), (4, 8, 1), (64, 8, 1), (256, 8, 1), (16, 6, 1),
-                                       (16, 9, 1), (2, 7, 1), (1, 8, 1)])
+                                       (16, 6, 0), (16, 7, 1), (16, 9, 1), (2, 7, 1), (1, 8, 1)])
 def test_c1_sweep(scpd, par, q, ext, prune):
     name, n, k, snr = CONFIG_SETS["c1"]
     llr = _llrs(par * 100 + q * 10 + ext, n, 400, k, snr)
     _check(scpd, name, n, k, par, q, ext, prune, llr)
+
+
+@pytest.mark.parametrize("prune", [0, 2])
+@pytest.mark.parametrize("par,q,ext", [(16, 6, 1), (16, 6, 0), (64, 6, 1), (64, 7, 1), (16, 8, 1), (16, 8, 0)])
+def test_sigmag_sweep(scpd, par, q, ext, prune):
+    """SIGMAG number format (config.h:11; the reference's checked-in default is SIGMAG, LLR_BITS 6): signed
+    zero, tie rule of qfull_add_sub_sm, half-range saturation of g."""
+    for key, nfr in (("c1", 300), ("c2", 70)):
+        name, n, k, snr = CONFIG_SETS[key]
+        llr = _llrs(par + q + ext, n, nfr, k, snr).copy()
+        llr[-1] = 0
+        llr[-2][::3] = 0
+        _check(scpd, name, n, k, par, q, ext, prune, llr, fmt=scpd.FMT_SIGMAG)
+
+
+def test_sigmag_differs_from_ca2_and_unsupported_combinations(scpd):
+    """The two formats give different codewords on noisy frames (so the format is part of the contract),
+    and a SIGMAG configuration without an instantiated kernel is refused, not approximated."""
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    llr = _llrs(77, n, 400, k, 1.0)
+    out = []
+    for fmt in (scpd.FMT_CA2, scpd.FMT_SIGMAG):
+        dec = scpd.Decoder(n, k, flags, par=16, llr_bits=6, fmt=fmt, extended=1)
+        out.append(dec.decode_host(llr))
+    assert (out[0] != out[1]).any()
+    with pytest.raises(scpd.ScpdError) as e:
+        scpd.Decoder(n, k, flags, par=4, llr_bits=9, fmt=scpd.FMT_SIGMAG, extended=1)
+    assert e.value.status == scpd.E_UNSUPPORTED
 
 
 def test_c1_headline_many_frames(scpd):
