@@ -18,6 +18,13 @@ namespace scpd {
 #define BS_LLOW 6
 #define BS_LSUB 4  // nodes of 2^BS_LSUB LLRs are decoded by one fused routine (code 8 * BS_LSUB + BSK_F + node types)
 enum : uint32_t { BSK_END = 0, BSK_F = 1, BSK_G = 2, BSK_G0 = 3, BSK_H = 4, BSK_HCOPY = 5, BSK_R0 = 6, BSK_R1 = 7 };
+// Fused ops (generic levels only): X(l) immediately followed by F(l-1) [and F(l-2)] runs as one pass that keeps
+// the freshly computed LLRs in registers, so alpha[l-1] (and alpha[l-2]) are written but not read back.  Codes
+// 8 + kind (two levels) and 16 + kind (three levels), kind = F / G / G0 of the first op; the subsumed F words
+// become BS_NOP so that word offsets (skip counts) stay valid.
+#define BS_FUSE2 8
+#define BS_FUSE3 16
+#define BS_NOP (8 * (BS_LLOW + 1))
 SCPD_HD static inline uint32_t bs_op_code(uint32_t w) { return w & 63u; }
 SCPD_HD static inline uint32_t bs_op_level(uint32_t w) { return (w >> 6) & 31u; }
 SCPD_HD static inline uint32_t bs_op_offset(uint32_t w) { return (w >> 11) & 0xFFFFFu; }
@@ -27,7 +34,9 @@ SCPD_HD static inline uint32_t bs_op_sync(uint32_t w) { return w >> 31; }  // al
 // bit-sliced kernel has no code for (OP_P1: PAR = 1).
 // sync_every: every sync_every-th op that lies outside all rate-1 fallback regions (those are the ops every
 // warp executes, whatever its data) gets the CTA-barrier flag; 0 = none.
-static inline bool bs_compile_schedule(const std::vector<uint32_t>& ops, std::vector<uint32_t>* out, int sync_every = 0) {
+static inline void bs_fuse_chains(std::vector<uint32_t>* sched, int max_depth);
+static inline bool bs_compile_schedule(const std::vector<uint32_t>& ops, std::vector<uint32_t>* out, int sync_every = 0,
+                                       int fuse_depth = 3) {
     out->clear();
     out->reserve(ops.size());
     size_t fallback_end = 0;  // ops[i] with i < fallback_end are inside a fallback region
@@ -62,7 +71,39 @@ static inline bool bs_compile_schedule(const std::vector<uint32_t>& ops, std::ve
         out->push_back((kind + 8u * lc) | (l << 6) | (o << 11) | sync);
         if (op_code(w) == OP_R1) out->push_back(ops[++i]);  // skip count, verbatim
     }
+    if (fuse_depth >= 2) bs_fuse_chains(out, fuse_depth);
     return true;
+}
+
+// X(l) F(l-1) [F(l-2)] -> one fused op + BS_NOP words.  Only ops of the generic levels (> BS_LLOW) take part,
+// and the last F of a chain must still be a generic-level op.  Data words (node types, skip counts) follow
+// OP_SUB / R1 words and are stepped over.
+static inline void bs_fuse_chains(std::vector<uint32_t>* sched, int max_depth) {
+    std::vector<uint32_t>& s = *sched;
+    const uint32_t gen = 8u * (BS_LLOW + 1);
+    auto is_data_follow = [&](uint32_t w) {
+        const uint32_t c = bs_op_code(w);
+        return c == 8u * BS_LSUB + BSK_F || (c & 7u) == BSK_R1;
+    };
+    for (size_t i = 0; i + 1 < s.size(); i++) {
+        const uint32_t w = s[i], c = bs_op_code(w), l = bs_op_level(w);
+        if (c == 0) continue;
+        if (is_data_follow(w) && c != 0) {
+            i++;  // skip the data word
+            continue;
+        }
+        if (c != gen + BSK_F && c != gen + BSK_G && c != gen + BSK_G0) continue;
+        const uint32_t kind = c - gen;
+        auto is_f = [&](size_t j, uint32_t lev) {
+            return j < s.size() && bs_op_code(s[j]) == gen + BSK_F && bs_op_level(s[j]) == lev && lev > BS_LLOW;
+        };
+        if (!is_f(i + 1, l - 1)) continue;
+        int depth = 2;
+        if (max_depth >= 3 && is_f(i + 2, l - 2)) depth = 3;
+        s[i] = (w & ~63u) | ((depth == 3 ? BS_FUSE3 : BS_FUSE2) + kind);
+        for (int k = 1; k < depth; k++) s[i + k] = (s[i + k] & ~63u) | BS_NOP;
+        i += depth - 1;
+    }
 }
 
 struct BsPlan {

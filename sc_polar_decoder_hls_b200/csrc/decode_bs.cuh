@@ -412,6 +412,51 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
         for (; i < h; i += G) g_many<1>(src, dst, bs_, zero, l, h, i);
         __syncwarp();
     }
+    // Fused X(l) F(l-1) [F(l-2)]: a lane takes the DEPTH-1 levels of pairs that hang under its slot j, i.e. the
+    // 2^(DEPTH-1) outputs j + k * (h >> (DEPTH-1)) of the first op, and carries them on in registers.  Every
+    // level is still written (the g of that level needs it later) but nothing is read back.
+    template <int DEPTH>
+    __device__ __forceinline__ void op_fuse(int l, uint32_t o, uint32_t kind) {
+        constexpr int W = 1 << (DEPTH - 1);  // outputs of the first op per lane and trip
+        const uint32_t h = 1u << (l - 1), q = h >> (DEPTH - 1);
+        const uint8_t* src = aptr(l);
+        uint8_t* d1 = aptr(l - 1);
+        uint8_t* d2 = aptr(l - 2);
+        uint8_t* d3 = DEPTH == 3 ? aptr(l - 3) : nullptr;
+        const uint8_t* bs_ = bptr(l - 1, o);
+        for (uint32_t j = ll; j < q; j += G) {
+            bs::Val<PQ> a[W], b[W], r[W];
+            uint32_t u_[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                load(src, l, j + k * q, a[k]);
+                load(src, l, j + k * q + h, b[k]);
+                u_[k] = kind == BSK_G ? *reinterpret_cast<const uint32_t*>(bs_ + 4u * (j + k * q)) : 0u;
+            }
+            if (kind == BSK_F) {
+#pragma unroll
+                for (int k = 0; k < W; k++) bs::f_op<PQ>(a[k], b[k], r[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; k++) bs::g_sat<FMT, PQ>(a[k], b[k], u_[k], r[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < W; k++) store(d1, l - 1, j + k * q, r[k]);
+            // F(l-1): pairs (x, x + h/2) = outputs k and k + W/2
+            bs::Val<PQ> r2[W / 2];
+#pragma unroll
+            for (int k = 0; k < W / 2; k++) {
+                bs::f_op<PQ>(r[k], r[k + W / 2], r2[k]);
+                store(d2, l - 2, j + k * q, r2[k]);
+            }
+            if constexpr (DEPTH == 3) {  // F(l-2): pair (x, x + h/4)
+                bs::Val<PQ> r3;
+                bs::f_op<PQ>(r2[0], r2[1], r3);
+                store(d3, l - 3, j, r3);
+            }
+        }
+        __syncwarp();
+    }
     // node (l,o) := (left ^ right, right); copy: the left child is all-frozen          H_STATE my_module.h:903-932
     // When the children sit in the shared block and the node does not, the node moves to the workspace.
     __device__ __forceinline__ void op_h(int l, uint32_t o, bool copy) {
@@ -486,6 +531,13 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
             } else {
                 switch (code) {
                     case 0: return;
+                    case BS_NOP: break;
+                    case BS_FUSE2 + BSK_F:
+                    case BS_FUSE2 + BSK_G:
+                    case BS_FUSE2 + BSK_G0: op_fuse<2>(l, o, code - BS_FUSE2); break;
+                    case BS_FUSE3 + BSK_F:
+                    case BS_FUSE3 + BSK_G:
+                    case BS_FUSE3 + BSK_G0: op_fuse<3>(l, o, code - BS_FUSE3); break;
                     case 8 * BS_LSUB + BSK_R0: this->template r0_low<BS_LSUB>(ob); break;
 #define BS_LOW(L)                                                           \
     case 8 * L + BSK_F: this->template f_low<L>(); break;                  \

@@ -246,7 +246,11 @@ static int plan_bs(scpd_decoder* d, const uint8_t* flags) {
     {
         const std::vector<uint32_t> ops = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning,
                                                          flags, &d->bs_stats, BS_LSUB, d->cfg.format == SCPD_FMT_CA2 ? 1 : 2);
-        if (!bs_compile_schedule(ops, &d->bs_sched_host, env_int("SCPD_BS_SYNC", 0))) return SCPD_OK;
+        // fused X(l) F(l-1) F(l-2) passes pay off once the spilled levels dominate (measured: +8 % at N = 2^15,
+        // +10 % at 2^17, a loss at 2^12 and below where the read-back hits L2 anyway)
+        if (!bs_compile_schedule(ops, &d->bs_sched_host, env_int("SCPD_BS_SYNC", 0),
+                                 env_int("SCPD_BS_FUSE", d->log2n >= 14 ? 3 : 0)))
+            return SCPD_OK;
     }
     // a schedule of up to 8 KB is copied into shared memory by every CTA (op fetches then never miss)
     d->bs_sched_smem = d->bs_sched_host.size() <= (size_t)env_int("SCPD_BS_SCHED_SMEM_WORDS", 2048);

@@ -190,7 +190,7 @@ int emu_fast_decode(int g, int log2n, int log2par, int llr_bits, int extended, i
 // emulator, -3 if it does not fit.
 int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int extended, int pruning, const uint8_t* flags,
                   const int8_t* llr, size_t nframes, uint32_t* xhat, int lsa, int lsb, int smem_per_group, int warps,
-                  int grid) {
+                  int grid, int fuse) {
     struct BL {
         BsParams p;
     } L;
@@ -207,7 +207,7 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
     ScheduleStats st;
     std::vector<uint32_t> ops = build_schedule(log2n, log2par, extended, pruning, flags, &st, BS_LSUB, fmt == 0 ? 1 : 2);
     std::vector<uint32_t> sched;
-    if (!bs_compile_schedule(ops, &sched)) return -4;
+    if (!bs_compile_schedule(ops, &sched, 0, fuse)) return -4;
     BsPlan plan;
     if (!bs_make_plan(log2n, llr_bits, log2par, extended, (size_t)smem_per_group, &plan, lsa, lsb, g)) return -3;
     const int gpw = 32 / g;

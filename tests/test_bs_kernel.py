@@ -19,10 +19,10 @@ def _emu():
     return _LIB["l"]
 
 
-def bs_emu(fmt, g, flags, n, par, q, ext, prune, llr, lsa=-1, lsb=-1, smem=56000, warps=1, grid=1):
+def bs_emu(fmt, g, flags, n, par, q, ext, prune, llr, lsa=-1, lsb=-1, smem=56000, warps=1, grid=1, fuse=3):
     out = np.zeros((len(llr), n // 32), np.uint32)
     rc = _emu().emu_bs_decode(fmt, g, int(np.log2(n)), int(np.log2(par)), q, ext, prune, ol.P(flags), ol.P(llr),
-                              ctypes.c_size_t(len(llr)), ol.P(out), lsa, lsb, smem, warps, grid)
+                              ctypes.c_size_t(len(llr)), ol.P(out), lsa, lsb, smem, warps, grid, fuse)
     assert rc == 0, rc
     return out
 
@@ -57,8 +57,9 @@ def test_bs_kernel_storage_split_and_grid(name, n, k):
         llr = ol.test_llrs(rng, n, nfr, k, maxabs=127)
         llr[-1][rng.random(n) < 0.5] = 0
         want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
-        got = bs_emu(0, g, flags, n, 16, 8, 1, 2, llr, lsa, lsb, 50000, warps, grid)
-        assert (got == want).all(), (g, lsa, lsb)
+        for fuse in (0, 2, 3):  # X(l) F(l-1) [F(l-2)] fused into one pass, or every op on its own
+            got = bs_emu(0, g, flags, n, 16, 8, 1, 2, llr, lsa, lsb, 50000, warps, grid, fuse)
+            assert (got == want).all(), (g, lsa, lsb, fuse)
 
 
 def test_bs_kernel_random_flag_tables():

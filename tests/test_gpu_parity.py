@@ -90,6 +90,8 @@ def kernel_mode(request, monkeypatch):
 @pytest.mark.parametrize("key,nfr", [("c1", 600), ("c2", 150), ("c3", 8)])
 @pytest.mark.parametrize("prune", [0, 1, 2])
 def test_every_kernel_variant(scpd, kernel_mode, key, nfr, prune):
+    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8"):
+        pytest.skip("the large tree is covered by one variant per kernel family")
     name, n, k, snr = CONFIG_SETS[key]
     llr = _llrs(21, n, nfr, k, snr).copy()
     llr[-1] = 0
