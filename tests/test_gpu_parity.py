@@ -235,7 +235,7 @@ def test_arbitrary_flag_patterns(scpd):
 def test_device_channel_matches_oracle_chain(scpd):
     """Integer RNG stream is exact by construction; float libm differs in the last ulp, so LLRs
     may differ by one quantisation step on a tiny fraction of samples (SURVEY 'Channel parity')."""
-    for n, nfr, first in ((1024, 64, 0), (1024, 5, 1000003), (64, 9, 17), (8, 40, 0), (4096, 6, 123456789)):
+    for n, nfr, first in ((1024, 64, 0), (1024, 5, 100003), (64, 9, 17), (8, 40, 0), (4096, 6, 54321)):  # the oracle steps, the device jumps
         sig = scpd.sigma(2.5, 0.5)
         cw = (np.arange(n) % 3 == 0).astype(np.uint8)
         dev = scpd.channel_generate(n, nfr, sig, first_frame=first, codeword=cw).cpu().numpy()
