@@ -592,7 +592,12 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     if (!d_llr || !d_xhat) return set_error(SCPD_E_ARG, "scpd_decode: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->bs_ok && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0) return decode_bs(d, d_llr, nframes, d_xhat, st);
+    // One warp walks the tree of a 32-frame group alone: a batch of fewer than two groups per SM leaves the GPU
+    // idle, and the int16x2 kernel (2 frames per lane group) is the better choice when it is available.
+    const bool bs_small = d->fast_group && d->cfg.format == SCPD_FMT_CA2 && !std::getenv("SCPD_KERNEL") &&
+                          (nframes + 31) / 32 < 2ull * (unsigned long long)d->num_sms && d->log2n >= 14;
+    if (d->bs_ok && !bs_small && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0)
+        return decode_bs(d, d_llr, nframes, d_xhat, st);
     if (d->cfg.format != SCPD_FMT_CA2)
         return set_error(SCPD_E_ARG, "scpd_decode: SIGMAG needs a 4-byte aligned LLR buffer");
     if (d->fast_group && (reinterpret_cast<uintptr_t>(d_llr) & 7u) == 0) return decode_fast(d, d_llr, nframes, d_xhat, st);

@@ -19,8 +19,8 @@ import sc_polar_decoder_hls_b200 as scpd
 
 SETS = {"c1": ("FB_N1024_K512", 1024, 512, 2.5, 1 << 20), "c2": ("frozen_n_4096_k_3072", 4096, 3072, 3.5, 1 << 20),
         "c3": ("frozen_n_32768_k_29492_snr_4_5", 32768, 29492, 4.5, 1 << 16),
-        "c4": ("frozen_n_131072_k_117964", 131072, 117964, 4.5, 1 << 14),
-        "c5": ("frozen_n_524288_k_262144", 524288, 262144, 2.0, 1 << 14)}
+        "c4": ("frozen_n_131072_k_117964", 131072, 117964, 4.5, 1 << 16),
+        "c5": ("frozen_n_524288_k_262144", 524288, 262144, 2.0, 1 << 15)}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--cfgs", default="c1,c2,c3,c4,c5")
