@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -205,12 +205,12 @@ def run_gpu_arm(a):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a moment to start: the warm-up below is under load too
     for _ in range(a.warmup):
         dec.decode(llr, xhat)
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     launches0 = dec.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -251,6 +251,7 @@ def run_gpu_arm(a):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
     e2e_val = world * (hi - lo) * k / (e2e_ms * 1e-3) / 1e9
     assert (h_out[:chk].numpy().view(np.uint32) == want).all()
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device-resident and the end-to-end regions
 
     if rank == 0:
         peaks = {}

@@ -74,6 +74,14 @@ public:
         check(scpd_run_ber(h_, ebn0_db, rate, first_frame, nframes, seed, codeword, c));
         return BerCounters{c[0], c[1], c[2], c[3], c[4], c[5]};
     }
+    // measurement aids (sc_monitor's role): duration of the tree-walk kernel of the last decode, kernel in use
+    void kernel_timing(bool on) { check(scpd_kernel_timing(h_, on ? 1 : 0)); }
+    float last_kernel_ms() {
+        float ms = 0.f;
+        check(scpd_last_kernel_ms(h_, &ms));
+        return ms;
+    }
+    std::string kernel_name() const { return scpd_kernel_name(h_); }
     scpd_decoder* handle() { return h_; }
 
 private:

@@ -270,4 +270,17 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
     }
     return 0;
 }
+
+// The compiled op words of the bit-sliced kernel (host logic under test).  Returns the number of words,
+// or a negative code; at most `cap` words are copied to `out`.
+long long emu_bs_schedule(int fmt, int log2n, int log2par, int extended, int pruning, const uint8_t* flags, int fuse,
+                          uint32_t* out, size_t cap, uint32_t* generic_words) {
+    ScheduleStats st;
+    std::vector<uint32_t> ops = build_schedule(log2n, log2par, extended, pruning, flags, &st, BS_LSUB, fmt == 0 ? 1 : 2);
+    std::vector<uint32_t> sched;
+    if (!bs_compile_schedule(ops, &sched, 0, fuse)) return -4;
+    if (generic_words) *generic_words = (uint32_t)ops.size();
+    for (size_t i = 0; i < sched.size() && i < cap; i++) out[i] = sched[i];
+    return (long long)sched.size();
+}
 }

@@ -72,3 +72,48 @@ def test_bs_kernel_random_flag_tables():
                 want = ol.decode_packed(n, 16, q, fmt, 1, flags, llr)
                 for prune in (0, 2):
                     assert (bs_emu(fmt, g, flags, n, 16, q, 1, prune, llr) == want).all(), (n, fmt, prune)
+
+
+def test_bs_schedule_compiler_invariants():
+    """Host logic of csrc/bs_plan.h: one word per word of the generic schedule (so the skip counts behind an
+    all-information node stay valid), fused passes only on generic levels and followed by exactly the no-op
+    words they subsume, and no skip ever lands on a no-op."""
+    lib = _emu()
+    lib.emu_bs_schedule.restype = ctypes.c_longlong
+    LLOW, LSUB, NOP = 6, 4, 8 * 7
+    for name, n in (("FB_N1024_K512", 1024), ("frozen_n_4096_k_3072", 4096), ("frozen_n_32768_k_29492_snr_4_5", 32768)):
+        flags = scpd.packed_flags(name, n)
+        for fmt in (0, 1):
+            for fuse in (0, 2, 3):
+                buf = np.zeros(1 << 18, np.uint32)
+                gw = ctypes.c_uint32()
+                m = lib.emu_bs_schedule(fmt, int(np.log2(n)), 4, 1, 2, ol.P(flags), fuse, ol.P(buf),
+                                        ctypes.c_size_t(len(buf)), ctypes.byref(gw))
+                assert m == gw.value and 0 < m <= len(buf)
+                w = buf[:m]
+                code, lev = w & 63, (w >> 6) & 31
+                i, targets, nfused = 0, set(), 0
+                while i < m:
+                    c = int(code[i])
+                    if c == 0:
+                        i += 1
+                    elif c == 8 * LSUB + 1:  # fused subtree + node types
+                        i += 2
+                    elif c % 8 == 7 and c >= 8 * 5:  # R1 of a specialised or generic level: skip count follows
+                        skip = int(w[i + 1])
+                        assert fmt == 0 or skip == 0
+                        targets.add(i + 2 + skip)
+                        i += 2
+                    elif c in (9, 10, 11, 17, 18, 19):  # X(l) F(l-1) [F(l-2)]
+                        depth = 2 if c < 16 else 3
+                        assert fuse >= depth and lev[i] - depth + 1 > LLOW
+                        for d in range(1, depth):
+                            assert code[i + d] == NOP and lev[i + d] == lev[i] - d
+                        nfused += 1
+                        i += depth
+                    else:
+                        assert c != NOP, "a no-op that no fused pass owns"
+                        i += 1
+                assert (nfused > 0) == (fuse >= 2)
+                for t in targets:
+                    assert t < m and code[t] != NOP
