@@ -331,11 +331,13 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
     __device__ __forceinline__ uint8_t* bptr(int l, uint32_t o) const {  // partial sums of node (l, o)
         return (uint32_t)l <= p.lsb ? smp_grp + p.sm_beta_off + ((4u * o) & bmask) : ws_grp + p.ws_beta_off + 4ull * o;
     }
-    __device__ __forceinline__ static void load(const uint8_t* base, int l, uint32_t i, bs::Val<PQ>& x) {
+    // p0: address of the slot in plane quad 0; qs: bytes between the plane quads of the level (16 << l).
+    // Callers keep p0 / qs in registers across a trip, so that the slots of a trip are immediate offsets.
+    __device__ __forceinline__ static void load(const uint8_t* p0, size_t qs, bs::Val<PQ>& x) {
         uint32_t w[4 * NVQ];
 #pragma unroll
         for (int v = 0; v < NVQ; v++) {
-            const uint4 t = *reinterpret_cast<const uint4*>(base + (((size_t)v << l) + i) * 16u);
+            const uint4 t = *reinterpret_cast<const uint4*>(p0 + v * qs);
             w[4 * v] = t.x;
             w[4 * v + 1] = t.y;
             w[4 * v + 2] = t.z;
@@ -345,16 +347,14 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
 #pragma unroll
         for (int k = 0; k < PQ; k++) x.m[k] = w[1 + k];
     }
-    __device__ __forceinline__ static void store(uint8_t* base, int l, uint32_t i, const bs::Val<PQ>& x) {
+    __device__ __forceinline__ static void store(uint8_t* p0, size_t qs, const bs::Val<PQ>& x) {
         uint32_t w[4 * NVQ];
         w[0] = x.s;
 #pragma unroll
         for (int k = 1; k < 4 * NVQ; k++) w[k] = (k <= PQ) ? x.m[k - 1] : 0u;
 #pragma unroll
-        for (int v = 0; v < NVQ; v++) {
-            *reinterpret_cast<uint4*>(base + (((size_t)v << l) + i) * 16u) =
-                make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-        }
+        for (int v = 0; v < NVQ; v++)
+            *reinterpret_cast<uint4*>(p0 + v * qs) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
     }
 
     // ------------------------------------------------------------ generic levels (nodes of 128 LLRs and more)
@@ -363,15 +363,19 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
     template <int U>
     __device__ __forceinline__ static void f_many(const uint8_t* src, uint8_t* dst, int l, uint32_t h, uint32_t i) {
         bs::Val<PQ> a[U], b[U], r[U];
+        const size_t qs = (size_t)16 << l;
+        const uint8_t* pa = src + (size_t)i * 16u;
+        const uint8_t* pb = pa + (size_t)h * 16u;
+        uint8_t* pd = dst + (size_t)i * 16u;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            load(src, l, i + u * G, a[u]);
-            load(src, l, i + u * G + h, b[u]);
+            load(pa + u * (G * 16), qs, a[u]);
+            load(pb + u * (G * 16), qs, b[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) bs::f_op<PQ>(a[u], b[u], r[u]);
 #pragma unroll
-        for (int u = 0; u < U; u++) store(dst, l - 1, i + u * G, r[u]);
+        for (int u = 0; u < U; u++) store(pd + u * (G * 16), qs >> 1, r[u]);
     }
     __device__ __forceinline__ void op_f(int l) {
         constexpr int U = SCPD_BS_U;
@@ -390,16 +394,21 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
                                                   uint32_t h, uint32_t i) {
         bs::Val<PQ> a[U], b[U], r[U];
         uint32_t u_[U];
+        const size_t qs = (size_t)16 << l;
+        const uint8_t* pa = src + (size_t)i * 16u;
+        const uint8_t* pb = pa + (size_t)h * 16u;
+        const uint8_t* pu = bs_ + (size_t)i * 4u;
+        uint8_t* pd = dst + (size_t)i * 16u;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            load(src, l, i + u * G, a[u]);
-            load(src, l, i + u * G + h, b[u]);
-            u_[u] = zero ? 0u : *reinterpret_cast<const uint32_t*>(bs_ + 4u * (i + u * G));
+            load(pa + u * (G * 16), qs, a[u]);
+            load(pb + u * (G * 16), qs, b[u]);
+            u_[u] = zero ? 0u : *reinterpret_cast<const uint32_t*>(pu + u * (G * 4));
         }
 #pragma unroll
         for (int u = 0; u < U; u++) bs::g_sat<FMT, PQ>(a[u], b[u], u_[u], r[u]);
 #pragma unroll
-        for (int u = 0; u < U; u++) store(dst, l - 1, i + u * G, r[u]);
+        for (int u = 0; u < U; u++) store(pd + u * (G * 16), qs >> 1, r[u]);
     }
     __device__ __forceinline__ void op_g(int l, uint32_t o, bool zero) {
         constexpr int U = SCPD_BS_U;
@@ -424,13 +433,15 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
         uint8_t* d2 = aptr(l - 2);
         uint8_t* d3 = DEPTH == 3 ? aptr(l - 3) : nullptr;
         const uint8_t* bs_ = bptr(l - 1, o);
+        const size_t qs = (size_t)16 << l, hs = (size_t)h * 16u, ks = (size_t)q * 16u;
         for (uint32_t j = ll; j < q; j += G) {
             bs::Val<PQ> a[W], b[W], r[W];
             uint32_t u_[W];
+            const uint8_t* pa = src + (size_t)j * 16u;
 #pragma unroll
             for (int k = 0; k < W; k++) {
-                load(src, l, j + k * q, a[k]);
-                load(src, l, j + k * q + h, b[k]);
+                load(pa + k * ks, qs, a[k]);
+                load(pa + k * ks + hs, qs, b[k]);
                 u_[k] = kind == BSK_G ? *reinterpret_cast<const uint32_t*>(bs_ + 4u * (j + k * q)) : 0u;
             }
             if (kind == BSK_F) {
@@ -441,18 +452,18 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
                 for (int k = 0; k < W; k++) bs::g_sat<FMT, PQ>(a[k], b[k], u_[k], r[k]);
             }
 #pragma unroll
-            for (int k = 0; k < W; k++) store(d1, l - 1, j + k * q, r[k]);
+            for (int k = 0; k < W; k++) store(d1 + (size_t)j * 16u + k * ks, qs >> 1, r[k]);
             // F(l-1): pairs (x, x + h/2) = outputs k and k + W/2
             bs::Val<PQ> r2[W / 2];
 #pragma unroll
             for (int k = 0; k < W / 2; k++) {
                 bs::f_op<PQ>(r[k], r[k + W / 2], r2[k]);
-                store(d2, l - 2, j + k * q, r2[k]);
+                store(d2 + (size_t)j * 16u + k * ks, qs >> 2, r2[k]);
             }
             if constexpr (DEPTH == 3) {  // F(l-2): pair (x, x + h/4)
                 bs::Val<PQ> r3;
                 bs::f_op<PQ>(r2[0], r2[1], r3);
-                store(d3, l - 3, j, r3);
+                store(d3 + (size_t)j * 16u, qs >> 3, r3);
             }
         }
         __syncwarp();
@@ -493,7 +504,7 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
         uint32_t z = 0u;
         for (uint32_t i = ll; i < (1u << l); i += G) {
             bs::Val<PQ> a;
-            load(src, l, i, a);
+            load(src + (size_t)i * 16u, (size_t)16 << l, a);
             uint32_t x = a.s;
             if (FMT == bs::FMT_CA2) {
                 const uint32_t nz = bs::nonzero<PQ>(a);
