@@ -66,6 +66,7 @@ struct BsParams {
     unsigned long long ws_stride;
     uint32_t ws_beta_off;
     uint32_t aoff[24];     // byte offset of alpha[l] inside the shared region (l <= lsa) or the workspace
+    uint32_t prefetch;     // 1: g asks L2 for its whole source level up front (pays off for small trees)
 };
 
 #if defined(__CUDACC__)
@@ -410,10 +411,24 @@ struct BsDecoder : BsLow<FMT, Q, LOG2PAR, EXT, G> {
 #pragma unroll
         for (int u = 0; u < U; u++) store(pd + u * (G * 16), qs >> 1, r[u]);
     }
+    // g reads a level that was written a whole subtree ago: when it lives in the workspace it has usually left
+    // L2, so one lane asks for the whole array up front and only the first trip pays the DRAM latency.
+    __device__ __forceinline__ void prefetch_alpha(const uint8_t* src, int l) const {
+#if defined(__CUDACC__) && !defined(SCPD_BS_NO_PREFETCH)
+        if (p.prefetch && (uint32_t)l > p.lsa && ll == 0) {
+            const uint32_t bytes = ((uint32_t)NVQ * 16u) << l;
+            for (uint32_t off = 0; off < bytes; off += 32768u) {
+                const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(n));
+            }
+        }
+#endif
+    }
     __device__ __forceinline__ void op_g(int l, uint32_t o, bool zero) {
         constexpr int U = SCPD_BS_U;
         const uint32_t h = 1u << (l - 1);
         const uint8_t* src = aptr(l);
+        prefetch_alpha(src, l);
         uint8_t* dst = aptr(l - 1);
         const uint8_t* bs_ = bptr(l - 1, o);
         uint32_t i = ll;

@@ -577,6 +577,8 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.ws_stride = d->bs_plan.ws_stride;
     p.ws_beta_off = d->bs_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->bs_plan.aoff[l];
+    // measured: +5 % at N = 1024 (latency of the read-back), -2 % at N = 4096 (already short of DRAM bandwidth)
+    p.prefetch = (uint32_t)env_int("SCPD_BS_PREFETCH", d->log2n <= 11 ? 1 : 0);
     bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->bs_group);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(d->bs_warps * 32)), d->bs_smem_bytes, st>>>(p);

@@ -214,6 +214,7 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
     if ((size_t)plan.sm_stride * warps * gpw > sizeof(smem_fast)) return -3;
     BsParams& p = L.p;
     p.sched = sched.data();
+    p.prefetch = 0;
     p.sched_words = 0;  // the emulator runs the warps of a CTA one after the other: no __syncthreads
     p.xhat = xhat;
     p.nframes = nframes;
