@@ -130,6 +130,7 @@ struct scpd_decoder {
     bool bs_ok = false;
     int bs_group = 8, bs_warps = 2, bs_ctas_per_sm = 1;
     bool bs_sched_smem = false;
+    bool kernel_pinned = false;  // SCPD_KERNEL was set when the handle was created
     BsPlan bs_plan;
     std::vector<uint32_t> bs_sched_host;
     ScheduleStats bs_stats;
@@ -204,12 +205,14 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
     BS_K(0, 8, 4, false, 32)
     BS_K(0, 7, 4, true, 32)
     BS_K(0, 6, 4, true, 32)
+    BS_K(0, 6, 4, true, 16)
     BS_K(0, 6, 4, false, 32)
     BS_K(0, 8, 2, true, 32)
     BS_K(0, 8, 6, true, 32)
     BS_K(0, 7, 1, true, 32)
     // SIGMAG (the reference's checked-in default is SIGMAG, LLR_BITS 6: config.h:2,11)
     BS_K(1, 6, 4, true, 32)
+    BS_K(1, 6, 4, true, 16)
     BS_K(1, 6, 4, false, 32)
     BS_K(1, 6, 6, true, 32)
     BS_K(1, 7, 6, true, 32)
@@ -419,6 +422,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
         return cuda_fail(e, "cudaGetDeviceProperties");
     }
     d->num_sms = prop.multiProcessorCount;
+    d->kernel_pinned = std::getenv("SCPD_KERNEL") != nullptr;
     int rc = plan_layout(d);
     if (rc == SCPD_OK) rc = plan_fast(d, flags);
     if (rc == SCPD_OK) rc = plan_bs(d, flags);
@@ -596,7 +600,7 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     cudaStream_t st = (cudaStream_t)stream;
     // One warp walks the tree of a 32-frame group alone: a batch of fewer than two groups per SM leaves the GPU
     // idle, and the int16x2 kernel (2 frames per lane group) is the better choice when it is available.
-    const bool bs_small = d->fast_group && d->cfg.format == SCPD_FMT_CA2 && !std::getenv("SCPD_KERNEL") &&
+    const bool bs_small = d->fast_group && d->cfg.format == SCPD_FMT_CA2 && !d->kernel_pinned &&
                           (nframes + 31) / 32 < 2ull * (unsigned long long)d->num_sms && d->log2n >= 14;
     if (d->bs_ok && !bs_small && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0)
         return decode_bs(d, d_llr, nframes, d_xhat, st);
@@ -698,6 +702,7 @@ extern "C" int scpd_decode_host(scpd_decoder* d, const int8_t* h_llr, size_t nfr
     CUDA_TRY(cudaSetDevice(d->device));
     const size_t n = d->cfg.n, row_out = (size_t)d->wpf * 4;
     size_t chunk = ((size_t)env_int("SCPD_HOST_CHUNK_MB", 256) << 20) / n;
+    chunk = std::max<size_t>(chunk, (size_t)64 * 32 * (size_t)d->num_sms / 16);  // >= 4 frame groups per SM per chunk
     chunk = std::max<size_t>(32, chunk & ~(size_t)31);
     if (chunk > nframes) chunk = nframes;
     int rc = ensure_pipeline(d, chunk);
@@ -824,8 +829,9 @@ extern "C" int scpd_run_ber(scpd_decoder* d, float ebn0_db, float rate, uint64_t
     if (!d || !h_counters) return set_error(SCPD_E_ARG, "scpd_run_ber: null argument");
     CUDA_TRY(cudaSetDevice(d->device));
     const uint32_t n = d->cfg.n;
-    // batch so that LLR staging stays around 1 GiB
+    // batch so that LLR staging stays around 1 GiB, but never fewer than 4 frame groups per SM (large trees)
     size_t batch = (size_t)((1ull << 30) / n);
+    batch = std::max<size_t>(batch, (size_t)4 * 32 * (size_t)d->num_sms);
     if (batch < 2) batch = 2;
     if (batch > nframes) batch = (size_t)nframes;
     if (batch == 0) {
