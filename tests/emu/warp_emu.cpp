@@ -5,6 +5,7 @@
 #include <ucontext.h>
 
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -283,5 +284,57 @@ long long emu_bs_schedule(int fmt, int log2n, int log2par, int extended, int pru
     if (generic_words) *generic_words = (uint32_t)ops.size();
     for (size_t i = 0; i < sched.size() && i < cap; i++) out[i] = sched[i];
     return (long long)sched.size();
+}
+
+// Element functions of bs_arith.cuh on (sign, magnitude) inputs, 32 cases per call word (host logic under
+// test against the oracle's sco_f / sco_g / sco_g_ext).  op: 0 = f, 1 = g saturated, 2 = g un-saturated.
+// sa/ma/sb/mb/u: `count` entries; outputs sign and magnitude.  P = q - 1 magnitude planes.
+int emu_bs_prim(int fmt, int q, int op, size_t count, const uint8_t* sa, const uint32_t* ma, const uint8_t* sb,
+                const uint32_t* mb, const uint8_t* u, uint8_t* so, uint32_t* mo) {
+    auto run = [&](auto tag) {
+        constexpr int P = decltype(tag)::value;
+        for (size_t base = 0; base < count; base += 32) {
+            bs::Val<P> a{}, b{};
+            uint32_t uw = 0;
+            for (size_t k = 0; k < 32 && base + k < count; k++) {
+                a.s |= (uint32_t)(sa[base + k] & 1u) << k;
+                b.s |= (uint32_t)(sb[base + k] & 1u) << k;
+                uw |= (uint32_t)(u[base + k] & 1u) << k;
+                for (int p = 0; p < P; p++) {
+                    a.m[p] |= ((ma[base + k] >> p) & 1u) << k;
+                    b.m[p] |= ((mb[base + k] >> p) & 1u) << k;
+                }
+            }
+            bs::Val<P + 1> r{};
+            if (op == 0) {
+                bs::Val<P> t;
+                bs::f_op<P>(a, b, t);
+                bs::widen<P + 1, P>(t, r);
+            } else if (op == 1) {
+                bs::Val<P> t;
+                if (fmt == 0)
+                    bs::g_sat<bs::FMT_CA2, P>(a, b, uw, t);
+                else
+                    bs::g_sat<bs::FMT_SM, P>(a, b, uw, t);
+                bs::widen<P + 1, P>(t, r);
+            } else {
+                bs::g_ext<P>(a, b, uw, r);
+            }
+            for (size_t k = 0; k < 32 && base + k < count; k++) {
+                so[base + k] = (uint8_t)((r.s >> k) & 1u);
+                uint32_t m = 0;
+                for (int p = 0; p <= P; p++) m |= ((r.m[p] >> k) & 1u) << p;
+                mo[base + k] = m;
+            }
+        }
+    };
+    switch (q) {
+        case 5: run(std::integral_constant<int, 4>{}); break;
+        case 6: run(std::integral_constant<int, 5>{}); break;
+        case 7: run(std::integral_constant<int, 6>{}); break;
+        case 8: run(std::integral_constant<int, 7>{}); break;
+        default: return -1;
+    }
+    return 0;
 }
 }

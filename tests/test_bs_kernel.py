@@ -117,3 +117,37 @@ def test_bs_schedule_compiler_invariants():
                 assert (nfused > 0) == (fuse >= 2)
                 for t in targets:
                     assert t < m and code[t] != NOP
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("q", [6, 8])
+def test_bs_element_functions_exhaustive(fmt, q):
+    """bs_arith.cuh f / saturating g / un-saturated g against the oracle's element functions
+    (oracle/sc_oracle.c: sco_f, sco_g, sco_g_ext) on EVERY pair of Q-bit values and both partial-sum bits.
+    CA2: same numeric value (a zero may carry either sign internally); SIGMAG: same (sign, magnitude) pattern."""
+    L = ol.lib()
+    P = q - 1
+    if fmt == 0:
+        vals = np.arange(-(2 ** P - 1), 2 ** P)
+        sgn, mag = (vals < 0).astype(np.uint8), np.abs(vals).astype(np.uint32)
+        pat = (vals & (2 ** q - 1)).astype(np.uint32)
+    else:
+        pat = np.arange(2 ** q, dtype=np.uint32)
+        sgn, mag = (pat >> P).astype(np.uint8), (pat & (2 ** P - 1)).astype(np.uint32)
+    ia, ib, iu = np.meshgrid(np.arange(len(pat)), np.arange(len(pat)), np.arange(2), indexing="ij")
+    ia, ib, iu = ia.ravel(), ib.ravel(), iu.ravel().astype(np.uint8)
+    sa, ma, sb, mb = (np.ascontiguousarray(x) for x in (sgn[ia], mag[ia], sgn[ib], mag[ib]))
+    so, mo = np.zeros(len(ia), np.uint8), np.zeros(len(ia), np.uint32)
+    for op, fn, wout in ((0, L.sco_f, q), (1, L.sco_g, q), (2, L.sco_g_ext, q + 1)):
+        rc = _emu().emu_bs_prim(fmt, q, op, ctypes.c_size_t(len(ia)), ol.P(sa), ol.P(ma), ol.P(sb), ol.P(mb), ol.P(iu),
+                                ol.P(so), ol.P(mo))
+        assert rc == 0
+        step = max(1, len(ia) // 60000)  # the oracle is called element by element from Python: sample evenly
+        for i in range(0, len(ia), step):
+            a, b, u = int(pat[ia[i]]), int(pat[ib[i]]), int(iu[i])
+            want = fn(fmt, q, a, b) if op == 0 else fn(fmt, q, a, b, u)
+            if fmt == 0:
+                got = -int(mo[i]) if so[i] else int(mo[i])
+                assert got == L.sco_value(0, wout, want), (op, a, b, u)
+            else:
+                assert (int(so[i]) << (wout - 1)) | int(mo[i]) == want, (op, a, b, u)
