@@ -69,6 +69,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None  # window of the timed regions (perf_counter)
 
     def start(self):
         try:
@@ -82,17 +83,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         self.proc.terminate()
         self.th.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.05)]
+        if not rows:  # nvidia-smi was slower to start than the run: one direct sample right behind the load
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True, timeout=20).stdout
+                rows = [[c.strip() for c in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except (OSError, subprocess.SubprocessError):
+                rows = []
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -180,6 +195,9 @@ def run_gpu_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi can take seconds to start on a fresh box: launch it before the set-up work
     n, k = CFG["n"], CFG["k"]
     frames = a.frames
     flags = scpd.packed_flags(CFG["name"], n)
@@ -205,9 +223,7 @@ def run_gpu_arm(a):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()  # nvidia-smi needs a moment to start: the warm-up below is under load too
+    sampler.mark_start()  # samples from here on are under load: warm-up, timed region, kernel timing, end to end
     for _ in range(a.warmup):
         dec.decode(llr, xhat)
     barrier()
@@ -228,7 +244,6 @@ def run_gpu_arm(a):
         kms.append(dec.last_kernel_ms())
     dec.kernel_timing(False)
     kernel_ms = float(np.mean(kms))
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     ms_step = ms_total / a.steps
     value = world * (hi - lo) * k / (ms_step * 1e-3) / 1e9
@@ -251,6 +266,7 @@ def run_gpu_arm(a):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
     e2e_val = world * (hi - lo) * k / (e2e_ms * 1e-3) / 1e9
     assert (h_out[:chk].numpy().view(np.uint32) == want).all()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None  # sampled over the device-resident and the end-to-end regions
 
     if rank == 0:
