@@ -3,26 +3,27 @@
 // Why: the decoder's arithmetic is Q-bit (Q = 6..8) and every frame of a batch runs the same
 // control flow, so the natural SIMD axis on a GPU is the FRAME axis at bit granularity: a 32-bit
 // register holds one bit plane of one LLR for 32 frames, f / g / h become a few dozen LOP3s per 32
-// frames (f: 2P+1, g: 5P+4 for P magnitude planes) with no pack / unpack, no wasted SIMD half and
+// frames (f: 2P+1, g: 5P+2 for P magnitude planes) with no pack / unpack, no wasted SIMD half and
 // partial sums that are already packed (see bs_arith.cuh).
 //
 // Layout of the work
-//   * group = 32 consecutive frames; G lanes of a warp own one group from the int8 input rows to the
-//     packed output words (a warp decodes 32/G groups in lock step).  Lane i of the G works on LLR
+//   * group = 32 consecutive frames; G lanes of a warp own one group from its channel planes (written by
+//     bs_planes_kernel below) to the packed output words (a warp decodes 32/G groups in lock step).  Lane i of the G works on LLR
 //     "slot" i, i + G, ... of the node being processed, so the f / g pair (i, i + n/2) is lane-local
 //     for every node of 2G elements or more; smaller nodes use the first n/2 lanes and exchange
 //     through shared memory.
-//   * the host compiles the SC tree walk into one 32-bit word per node operation; operations on nodes
-//     of up to 64 LLRs have their level folded into the opcode so that each of them is a piece of
-//     straight-line code behind one jump table (sizes, plane counts and addresses are immediates).
+//   * the host compiles the SC tree walk into one 32-bit word per node operation (bs_plan.h).  A subtree of
+//     16 LLRs is ONE op that walks its 15 nodes from a word of 2-bit node types; ops on nodes of 32 / 64
+//     LLRs have their level folded into the opcode (sizes, plane counts and shared-memory addresses are
+//     immediates); larger nodes run streaming loops, optionally fused over up to three levels.
 //   * alpha[l] (the 2^l LLRs a node of size 2^l receives): per LLR a vector of planes
 //     {sign, m0, m1, ...}, stored as uint4 "plane quads": quad v of slot i at byte (v << l + i) * 16.
-//     Levels <= lsa live in shared memory, larger ones (and the transposed channel LLRs) in a
-//     per-warp workspace that stays L2 resident for small N and streams from HBM for large N.
+//     Levels <= lsa live in shared memory, larger ones in a per-group workspace (L2 / HBM); the channel
+//     level has its own buffer, one set of planes per group of the batch.
 //   * beta (partial sums): one word per code position (32 frames), natural order; nodes up to level
 //     lsb in shared memory, larger ones in the workspace.
-//   * the int8 rows are turned into planes by 32x32 bit transposes in registers (4 LLRs x 8 planes
-//     per transpose), the final partial sums are turned into packed rows the same way.
+//   * bs_planes_kernel turns the int8 rows into planes by 32x32 bit transposes in registers (4 LLRs x 8
+//     planes per transpose); the final partial sums are turned into packed rows the same way.
 //
 // Bit-exactness: see bs_arith.cuh for f / g / leaf rules in both number formats.  Width growth inside
 // the PAR-wide leaf decoder when EXTENDED (Spec_P*_ext, functions.h:413-438...) is modelled by giving
