@@ -598,10 +598,12 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     if (!d_llr || !d_xhat) return set_error(SCPD_E_ARG, "scpd_decode: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
-    // One warp walks the tree of a 32-frame group alone: a batch of fewer than two groups per SM leaves the GPU
-    // idle, and the int16x2 kernel (2 frames per lane group) is the better choice when it is available.
+    // One warp walks the tree of a 32-frame group alone, so the bit-sliced kernel needs many groups to fill the
+    // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 16 k at N = 4096
+    // and 32768, far fewer for the largest trees) the int16x2 kernel with 2 frames per lane group is faster.
+    const unsigned long long bs_min_groups = d->log2n <= 11 ? 1536 : d->log2n <= 15 ? 512 : d->log2n <= 17 ? 128 : 64;
     const bool bs_small = d->fast_group && d->cfg.format == SCPD_FMT_CA2 && !d->kernel_pinned &&
-                          (nframes + 31) / 32 < 2ull * (unsigned long long)d->num_sms && d->log2n >= 14;
+                          (nframes + 31) / 32 < bs_min_groups;
     if (d->bs_ok && !bs_small && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0)
         return decode_bs(d, d_llr, nframes, d_xhat, st);
     if (d->cfg.format != SCPD_FMT_CA2)
