@@ -209,6 +209,8 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
     BS_K(0, 6, 4, false, 32)
     BS_K(0, 8, 2, true, 32)
     BS_K(0, 8, 6, true, 32)
+    BS_K(0, 7, 6, true, 32)
+    BS_K(0, 6, 6, true, 32)
     BS_K(0, 7, 1, true, 32)
     // SIGMAG (the reference's checked-in default is SIGMAG, LLR_BITS 6: config.h:2,11)
     BS_K(1, 6, 4, true, 32)
@@ -216,6 +218,8 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
     BS_K(1, 6, 4, false, 32)
     BS_K(1, 6, 6, true, 32)
     BS_K(1, 7, 6, true, 32)
+    BS_K(1, 7, 4, true, 32)
+    BS_K(1, 8, 6, true, 32)
     BS_K(1, 8, 4, true, 32)
     BS_K(1, 8, 4, false, 32)
 #else

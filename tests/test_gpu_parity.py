@@ -117,7 +117,7 @@ def test_golden_codewords_noiseless(scpd):
 
 @pytest.mark.parametrize("prune", [0, 1, 2])
 @pytest.mark.parametrize("par,q,ext", [(16, 8, 1), (16, 8, 0), (4, 8, 1), (64, 8, 1), (256, 8, 1), (16, 6, 1),
-                                       (16, 6, 0), (16, 7, 1), (16, 9, 1), (2, 7, 1), (1, 8, 1)])
+                                       (16, 6, 0), (16, 7, 1), (64, 7, 1), (64, 6, 1), (16, 9, 1), (2, 7, 1), (1, 8, 1)])
 def test_c1_sweep(scpd, par, q, ext, prune):
     name, n, k, snr = CONFIG_SETS["c1"]
     llr = _llrs(par * 100 + q * 10 + ext, n, 400, k, snr)
@@ -125,7 +125,8 @@ def test_c1_sweep(scpd, par, q, ext, prune):
 
 
 @pytest.mark.parametrize("prune", [0, 2])
-@pytest.mark.parametrize("par,q,ext", [(16, 6, 1), (16, 6, 0), (64, 6, 1), (64, 7, 1), (16, 8, 1), (16, 8, 0)])
+@pytest.mark.parametrize("par,q,ext", [(16, 6, 1), (16, 6, 0), (64, 6, 1), (64, 7, 1), (16, 7, 1), (16, 8, 1), (16, 8, 0),
+                                       (64, 8, 1)])
 def test_sigmag_sweep(scpd, par, q, ext, prune):
     """SIGMAG number format (config.h:11; the reference's checked-in default is SIGMAG, LLR_BITS 6): signed
     zero, tie rule of qfull_add_sub_sm, half-range saturation of g."""
