@@ -92,7 +92,10 @@ int scpd_create(const scpd_config* cfg, const uint8_t* h_info_flags, int device,
                 scpd_decoder** out);
 void scpd_destroy(scpd_decoder* dec);
 /* e -> s ports (my_module.h:34-35): decode nframes frames.
- * d_llr  : [nframes][n] int8, device.      d_xhat : [nframes][n/32] uint32, device. */
+ * d_llr  : [nframes][n] int8, device.      d_xhat : [nframes][n/32] uint32, device.
+ * Large batches run on the bit-sliced kernel (32 frames per register bit; the handle then keeps a
+ * bit-plane copy of the batch, nframes * n bytes, plus a workspace for the resident frame groups); batches
+ * too small to fill the GPU that way run on the int16x2 kernel.  Results are identical either way. */
 int scpd_decode(scpd_decoder* dec, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat,
                 void* cuda_stream);
 /* Same through host buffers (pinned or pageable): the batch is cut into chunks that flow through an
