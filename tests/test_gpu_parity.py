@@ -195,6 +195,38 @@ def test_zero_llr_fallback(scpd):
         _check(scpd, name, n, k, 16, 8, 1, prune, llr)
 
 
+@pytest.mark.parametrize("group", ["16", "32"])
+def test_bit_sliced_kernel_edge_cases(scpd, monkeypatch, group):
+    """The batch-size dispatch sends small batches to the int16x2 kernel, so the edge cases are repeated here
+    with the bit-sliced kernel pinned: arbitrary (non-polar) flag tables, zero-heavy and full-range LLRs
+    (the CA2 rate-1 fallback on almost every node), ragged last groups, one-frame batches."""
+    monkeypatch.setenv("SCPD_KERNEL", "bs")
+    monkeypatch.setenv("SCPD_BS_GROUP", group)
+    rng = np.random.default_rng(int(group))
+    for n in (128, 256, 1024):
+        for trial in range(3):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-127, 128, size=(77, n)).astype(np.int8)
+            llr[rng.random(llr.shape) < 0.3] = 0
+            llr[0] = 0
+            llr[1] = 127
+            llr[2] = -127
+            for prune in (0, 1, 2):
+                dec = scpd.Decoder(n, int(flags.sum()), flags, par=16, pruning=prune)
+                assert "bit-sliced" in dec.kernel_name
+                assert (dec.decode_host(llr) == ol.decode_packed(n, 16, 8, 0, 1, flags, llr)).all(), (n, trial, prune)
+                dec.close()
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    for fmt, q in ((scpd.FMT_CA2, 8), (scpd.FMT_SIGMAG, 6)):
+        dec = scpd.Decoder(n, k, flags, llr_bits=q, fmt=fmt)
+        for nfr in (1, 2, 31, 32, 33, 65, 257):
+            llr = ol.test_llrs(rng, n, nfr, k, snr)
+            llr[-1][::3] = 0
+            assert (dec.decode_host(llr) == ol.decode_packed(n, 16, q, fmt, 1, flags, llr)).all(), (fmt, nfr)
+        dec.close()
+
+
 def test_ragged_and_empty_batches(scpd):
     name, n, k, snr = CONFIG_SETS["c1"]
     flags = scpd.packed_flags(name, n)
