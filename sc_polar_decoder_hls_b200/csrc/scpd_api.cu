@@ -17,6 +17,7 @@
 #include "decode_bs.cuh"
 #include "decode_fast.cuh"
 #include "decode_generic.cuh"
+#include "decode_raw.cuh"
 #include "harness.cuh"
 #include "internal.h"
 #include "schedule.h"
@@ -140,6 +141,18 @@ struct scpd_decoder {
     size_t bs_ws_bytes = 0;
     uint8_t* d_bs_planes = nullptr;
     size_t bs_planes_bytes = 0;
+    // raw-pattern kernel plan (decode_raw.cuh): the configurations outside the in-range int16x2 / bit-sliced
+    // datapaths.  raw_only: it is the only kernel of this handle
+    bool raw_ok = false, raw_only = false;
+    int raw_group = 32, raw_ctas_per_sm = 1;
+    std::vector<uint32_t> raw_sched_host;
+    ScheduleStats raw_stats;
+    uint32_t* d_raw_sched = nullptr;
+    uint32_t raw_ls = 0, raw_beta_in_smem = 1, raw_sm_words = 0;
+    unsigned long long raw_ws_words = 0;
+    size_t raw_smem_bytes = 0;
+    uint32_t* d_raw_ws = nullptr;
+    size_t raw_ws_bytes = 0;
     // timing of the dominant kernel (scpd_kernel_timing)
     bool timing = false;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
@@ -343,6 +356,43 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
     return SCPD_OK;
 }
 
+static const void* raw_kernel_ptr(int group) {
+    return group == 8 ? (const void*)sc_decode_raw_kernel<8> : (const void*)sc_decode_raw_kernel<32>;
+}
+
+// Shared-memory / workspace layout of the raw-pattern kernel: one 32-bit word per LLR and frame.
+static int plan_raw(scpd_decoder* d, const uint8_t* flags) {
+    d->raw_ok = false;
+    // all-frozen nodes are pruned (identical for any input); the rate-1 shortcut is not (decode_raw.cuh)
+    d->raw_sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended,
+                                       std::min<int>((int)d->cfg.pruning, SCPD_PRUNE_R0), flags, &d->raw_stats);
+    d->raw_group = d->log2n <= 7 ? 8 : 32;
+    const int f_per_cta = d->warps_per_cta * (32 / d->raw_group);
+    const size_t per_frame_words = 100 * 1024 / 4 / f_per_cta;  // two CTAs per SM
+    int ls = 0;
+    for (int l = 0; l <= d->log2n - 1; l++)
+        if ((size_t)(2u << l) <= per_frame_words) ls = l;
+    d->raw_ls = (uint32_t)ls;
+    size_t words = (size_t)(2u << ls);
+    d->raw_beta_in_smem = (words + d->wpf <= per_frame_words) ? 1u : 0u;
+    if (d->raw_beta_in_smem) words += d->wpf;
+    d->raw_sm_words = (uint32_t)words;
+    d->raw_smem_bytes = words * 4 * f_per_cta;
+    const bool need_ws = ls < d->log2n - 1 || !d->raw_beta_in_smem;
+    d->raw_ws_words = need_ws ? (unsigned long long)d->cfg.n + d->wpf : 0ull;
+    const void* k = raw_kernel_ptr(d->raw_group);
+    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->raw_smem_bytes));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, d->warps_per_cta * 32, d->raw_smem_bytes));
+    if (occ < 1) return set_error(SCPD_E_CUDA, "raw-pattern decode kernel does not fit on an SM");
+    d->raw_ctas_per_sm = occ;
+    d->raw_ok = true;
+    if (env_int("SCPD_VERBOSE", 0))
+        fprintf(stderr, "[scpd] raw-pattern kernel: %d lanes/frame, alpha levels <=%d in smem, %zu B/CTA, %d CTAs/SM\n",
+                d->raw_group, ls, d->raw_smem_bytes, occ);
+    return SCPD_OK;
+}
+
 static int plan_layout(scpd_decoder* d) {
     const char* env = std::getenv("SCPD_GROUP");
     d->group = 32;
@@ -397,17 +447,18 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     if (cfg->extended > 1) return set_error(SCPD_E_CONFIG, "extended must be 0 or 1");
     if (cfg->llr_bits < 5 || cfg->llr_bits > 9)
         return set_error(SCPD_E_CONFIG, "llr_bits outside 5..9 (range swept by script/script_tests.sh)");
-    if (cfg->llr_bits < 6)
-        return set_error(SCPD_E_UNSUPPORTED,
-                         "llr_bits < 6: the +-31 quantiser alphabet wraps in the reference; no kernel for that yet");
+    if (par > 512) return set_error(SCPD_E_UNSUPPORTED, "par above 512 not supported");
     const int log2par = ilog2(par);
-    // widest value inside the un-saturated leaf must fit int16 (Q + log2 PAR bits incl. the final sum)
-    if (cfg->extended && cfg->llr_bits + (uint32_t)log2par > 16)
-        return set_error(SCPD_E_UNSUPPORTED, "llr_bits + log2(par) > 16 does not fit the int16x2 datapath");
-    if (cfg->format == SCPD_FMT_SIGMAG &&
-        (!bs_kernel_ptr(SCPD_FMT_SIGMAG, (int)cfg->llr_bits, log2par, (int)cfg->extended, 0) || n < 128))
-        return set_error(SCPD_E_UNSUPPORTED,
-                         "SIGMAG: no bit-sliced kernel instantiated for this (llr_bits, par, extended) or n < 128");
+    // Outside the in-range int16x2 / bit-sliced datapaths -> the raw-pattern kernel (decode_raw.cuh):
+    //  * llr_bits 5: the +-31 quantiser alphabet wraps modulo 2^5 in the reference (wrapper_in.h:33-34)
+    //  * un-saturated leaves wider than int16 (Q + log2 PAR bits incl. the final sum)
+    //  * SIGMAG without a bit-sliced instantiation for (llr_bits, par, extended), or n < 128
+    const char* ksel_raw = std::getenv("SCPD_KERNEL");
+    const bool raw_only =
+        cfg->llr_bits < 6 || (cfg->extended && cfg->llr_bits + (uint32_t)log2par > 16) ||
+        (cfg->format == SCPD_FMT_SIGMAG &&
+         (!bs_kernel_ptr(SCPD_FMT_SIGMAG, (int)cfg->llr_bits, log2par, (int)cfg->extended, 0) || n < 128)) ||
+        (ksel_raw && std::strcmp(ksel_raw, "raw") == 0);
 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
@@ -427,11 +478,16 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     }
     d->num_sms = prop.multiProcessorCount;
     d->kernel_pinned = std::getenv("SCPD_KERNEL") != nullptr;
-    int rc = plan_layout(d);
-    if (rc == SCPD_OK) rc = plan_fast(d, flags);
-    if (rc == SCPD_OK) rc = plan_bs(d, flags);
-    if (rc == SCPD_OK && cfg->format == SCPD_FMT_SIGMAG && !d->bs_ok)
-        rc = set_error(SCPD_E_UNSUPPORTED, "SIGMAG: the bit-sliced kernel does not fit this configuration");
+    d->raw_only = raw_only;
+    int rc = SCPD_OK;
+    if (!raw_only) {
+        rc = plan_layout(d);
+        if (rc == SCPD_OK) rc = plan_fast(d, flags);
+        if (rc == SCPD_OK) rc = plan_bs(d, flags);
+        if (rc == SCPD_OK && cfg->format == SCPD_FMT_SIGMAG && !d->bs_ok) d->raw_only = true;
+    }
+    // SIGMAG handles keep the raw-pattern kernel beside the bit-sliced one for mis-aligned LLR buffers
+    if (rc == SCPD_OK && (d->raw_only || cfg->format == SCPD_FMT_SIGMAG)) rc = plan_raw(d, flags);
     if (rc != SCPD_OK) {
         delete d;
         return rc;
@@ -444,6 +500,12 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
         e = cudaMalloc(&d->d_fast_sched, d->fast_sched_host.size() * sizeof(uint32_t));
         if (e == cudaSuccess)
             e = cudaMemcpy(d->d_fast_sched, d->fast_sched_host.data(), d->fast_sched_host.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && d->raw_ok) {
+        e = cudaMalloc(&d->d_raw_sched, d->raw_sched_host.size() * sizeof(uint32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(d->d_raw_sched, d->raw_sched_host.data(), d->raw_sched_host.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess && d->bs_ok) {
@@ -471,6 +533,8 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_bs_sched);
     cudaFree(d->d_bs_ws);
     cudaFree(d->d_bs_planes);
+    cudaFree(d->d_raw_sched);
+    cudaFree(d->d_raw_ws);
     for (int b = 0; b < 2; b++) {
         cudaFree(d->d_llr2[b]);
         cudaFree(d->d_xhat2[b]);
@@ -596,12 +660,54 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     return SCPD_OK;
 }
 
+static int decode_raw(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
+    const unsigned long long f_per_cta = (unsigned long long)d->warps_per_cta * (32 / d->raw_group);
+    unsigned long long grid = (nframes + f_per_cta - 1) / f_per_cta;
+    const unsigned long long max_grid = (unsigned long long)d->num_sms * d->raw_ctas_per_sm;
+    if (grid > max_grid) grid = max_grid;
+    const size_t ws_need = (size_t)(grid * f_per_cta * d->raw_ws_words * 4ull);
+    if (ws_need > d->raw_ws_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_raw_ws);
+        d->d_raw_ws = nullptr;
+        d->raw_ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&d->d_raw_ws, ws_need));
+        d->raw_ws_bytes = ws_need;
+    }
+    RawParams p;
+    p.sched = d->d_raw_sched;
+    p.llr = d_llr;
+    p.xhat = d_xhat;
+    p.nframes = nframes;
+    p.n = d->cfg.n;
+    p.log2n = (uint32_t)d->log2n;
+    p.wpf = d->wpf;
+    p.q = d->cfg.llr_bits;
+    p.sigmag = d->cfg.format == SCPD_FMT_SIGMAG ? 1u : 0u;
+    p.ls = d->raw_ls;
+    p.beta_in_smem = d->raw_beta_in_smem;
+    p.sm_words_per_frame = d->raw_sm_words;
+    p.ws = d->d_raw_ws;
+    p.ws_words_per_frame = d->raw_ws_words;
+    const dim3 g((unsigned)grid), b((unsigned)(d->warps_per_cta * 32));
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
+    if (d->raw_group == 8)
+        sc_decode_raw_kernel<8><<<g, b, d->raw_smem_bytes, st>>>(p);
+    else
+        sc_decode_raw_kernel<32><<<g, b, d->raw_smem_bytes, st>>>(p);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
 extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, void* stream) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_decode: null decoder");
     if (nframes == 0) return SCPD_OK;
     if (!d_llr || !d_xhat) return set_error(SCPD_E_ARG, "scpd_decode: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->raw_only) return decode_raw(d, d_llr, nframes, d_xhat, st);
     // One warp walks the tree of a 32-frame group alone, so the bit-sliced kernel needs many groups to fill the
     // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 16 k at N = 4096
     // and 32768, far fewer for the largest trees) the int16x2 kernel with 2 frames per lane group is faster.
@@ -610,8 +716,7 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
                           (nframes + 31) / 32 < bs_min_groups;
     if (d->bs_ok && !bs_small && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0)
         return decode_bs(d, d_llr, nframes, d_xhat, st);
-    if (d->cfg.format != SCPD_FMT_CA2)
-        return set_error(SCPD_E_ARG, "scpd_decode: SIGMAG needs a 4-byte aligned LLR buffer");
+    if (d->cfg.format != SCPD_FMT_CA2) return decode_raw(d, d_llr, nframes, d_xhat, st);  // mis-aligned LLR buffer
     if (d->fast_group && (reinterpret_cast<uintptr_t>(d_llr) & 7u) == 0) return decode_fast(d, d_llr, nframes, d_xhat, st);
     const int gpw = 32 / d->group;
     const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
@@ -757,7 +862,9 @@ extern "C" int scpd_last_kernel_ms(scpd_decoder* d, float* ms) {
 extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
     static thread_local char buf[96];
     if (!d) return "";
-    if (d->bs_ok)
+    if (d->raw_only)
+        snprintf(buf, sizeof buf, "sc_decode_raw_kernel (raw W-bit patterns, %d lanes per frame)", d->raw_group);
+    else if (d->bs_ok)
         snprintf(buf, sizeof buf, "sc_decode_bs_kernel (bit-sliced, %d lanes per 32-frame group, %d warps/CTA)", d->bs_group,
                  d->bs_warps);
     else if (d->fast_group)
@@ -787,7 +894,7 @@ extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
 }
 extern "C" int scpd_schedule_stats(const scpd_decoder* d, uint64_t* n_ops, uint64_t* n_fg) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_schedule_stats: null decoder");
-    const ScheduleStats& st = d->bs_ok ? d->bs_stats : d->fast_group ? d->fast_stats : d->stats;
+    const ScheduleStats& st = d->raw_only ? d->raw_stats : d->bs_ok ? d->bs_stats : d->fast_group ? d->fast_stats : d->stats;
     if (n_ops) *n_ops = st.n_ops;
     if (n_fg) *n_fg = st.n_f + st.n_g;
     return SCPD_OK;

@@ -13,6 +13,7 @@
 // keep this include after the fake runtime
 #include "../../sc_polar_decoder_hls_b200/csrc/decode_fast.cuh"
 #include "../../sc_polar_decoder_hls_b200/csrc/decode_bs.cuh"
+#include "../../sc_polar_decoder_hls_b200/csrc/decode_raw.cuh"
 #include "../../sc_polar_decoder_hls_b200/csrc/bs_plan.h"
 
 namespace scpd {
@@ -261,6 +262,51 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
     for (int l = 0; l < 24; l++) p.aoff[l] = plan.aoff[l];
     std::vector<uint8_t> ws((size_t)grid * warps * gpw * plan.ws_stride + 256, 0xCD);
     p.ws = reinterpret_cast<uint8_t*>(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
+    dim3 gd, bd;
+    gd.x = (unsigned)grid;
+    bd.x = (unsigned)warps * 32;
+    for (int b = 0; b < grid; b++) {
+        std::memset(smem_fast, 0xEE, sizeof(smem_fast));
+        dim3 bi;
+        bi.x = (unsigned)b;
+        for (int w = 0; w < warps; w++) cuda_emu::run_warp(body, &L, bi, gd, bd, w);
+    }
+    return 0;
+}
+
+// Emulates the raw-pattern kernel (decode_raw.cuh): any format / LLR_BITS / PAR / EXTENDED.  g = lanes per
+// frame (8 or 32); ls < 0: every alpha level in shared memory.  pruning is clamped to R0 as scpd_create does.
+int emu_raw_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int extended, int pruning, const uint8_t* flags,
+                   const int8_t* llr, size_t nframes, uint32_t* xhat, int ls, int beta_in_smem, int warps, int grid) {
+    struct RL {
+        RawParams p;
+    } L;
+    void (*body)(void*) = nullptr;
+    if (g == 8) body = [](void* a) { sc_decode_raw_kernel<8>(static_cast<RL*>(a)->p); };
+    if (g == 32) body = [](void* a) { sc_decode_raw_kernel<32>(static_cast<RL*>(a)->p); };
+    if (!body) return -1;
+    ScheduleStats st;
+    std::vector<uint32_t> sched = build_schedule(log2n, log2par, extended, pruning > 1 ? 1 : pruning, flags, &st);
+    RawParams& p = L.p;
+    p.sched = sched.data();
+    p.llr = llr;
+    p.xhat = xhat;
+    p.nframes = nframes;
+    p.n = 1u << log2n;
+    p.log2n = (uint32_t)log2n;
+    p.wpf = p.n >= 32 ? p.n / 32 : 1;
+    p.q = (uint32_t)llr_bits;
+    p.sigmag = fmt ? 1u : 0u;
+    if (ls < 0 || ls > log2n - 1) ls = log2n - 1;
+    if (log2n == 1) ls = 0;
+    p.ls = (uint32_t)ls;
+    p.beta_in_smem = beta_in_smem ? 1u : 0u;
+    p.sm_words_per_frame = (2u << ls) + (beta_in_smem ? p.wpf : 0u);
+    p.ws_words_per_frame = (unsigned long long)p.n + p.wpf;
+    const size_t f_per_cta = (size_t)warps * (32 / g);
+    if ((size_t)p.sm_words_per_frame * 4 * f_per_cta > sizeof(smem_fast)) return -3;
+    std::vector<uint32_t> ws((size_t)grid * f_per_cta * p.ws_words_per_frame + 16, 0xCDCDCDCDu);
+    p.ws = ws.data();
     dim3 gd, bd;
     gd.x = (unsigned)grid;
     bd.x = (unsigned)warps * 32;

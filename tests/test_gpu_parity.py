@@ -64,17 +64,17 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
     dec.close()
 
 
-@pytest.fixture(params=["auto", "generic", "fast2", "fast8", "fast16", "bs8", "bs16", "bs32", "bs32ws"])
+@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "bs8", "bs16", "bs32", "bs32ws"])
 def kernel_mode(request, monkeypatch):
     """Selects the decode kernel through the library's environment switches (read in scpd_create):
     the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
     workspace early, one warp per CTA), the int16x2 kernel with 2 / 8 / 16 lanes per frame pair, the
-    generic kernel, and the library's own choice."""
+    generic kernel, the raw-pattern kernel, and the library's own choice."""
     mode = request.param
     for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS"):
         monkeypatch.delenv(v, raising=False)
-    if mode == "generic":
-        monkeypatch.setenv("SCPD_KERNEL", "generic")
+    if mode in ("generic", "raw"):
+        monkeypatch.setenv("SCPD_KERNEL", mode)
     elif mode.startswith("fast"):
         monkeypatch.setenv("SCPD_KERNEL", "fast")
         monkeypatch.setenv("SCPD_GROUP", mode[4:])
@@ -139,8 +139,9 @@ def test_sigmag_sweep(scpd, par, q, ext, prune):
 
 
 def test_sigmag_differs_from_ca2_and_unsupported_combinations(scpd):
-    """The two formats give different codewords on noisy frames (so the format is part of the contract),
-    and a SIGMAG configuration without an instantiated kernel is refused, not approximated."""
+    """The two formats give different codewords on noisy frames (so the format is part of the contract);
+    a SIGMAG configuration without a bit-sliced instantiation runs on the raw-pattern kernel, and what no
+    kernel covers is refused, not approximated."""
     name, n, k, snr = CONFIG_SETS["c1"]
     flags = scpd.packed_flags(name, n)
     llr = _llrs(77, n, 400, k, 1.0)
@@ -149,9 +150,60 @@ def test_sigmag_differs_from_ca2_and_unsupported_combinations(scpd):
         dec = scpd.Decoder(n, k, flags, par=16, llr_bits=6, fmt=fmt, extended=1)
         out.append(dec.decode_host(llr))
     assert (out[0] != out[1]).any()
+    dec = scpd.Decoder(n, k, flags, par=4, llr_bits=9, fmt=scpd.FMT_SIGMAG, extended=1)
+    assert "raw" in dec.kernel_name
+    assert (dec.decode_host(llr) == ol.decode_packed(n, 4, 9, 1, 1, flags, llr, threads=8)).all()
+    n2 = 1 << 21
     with pytest.raises(scpd.ScpdError) as e:
-        scpd.Decoder(n, k, flags, par=4, llr_bits=9, fmt=scpd.FMT_SIGMAG, extended=1)
+        scpd.Decoder(n2, n2 // 2, np.tile(np.array([0, 1], np.uint8), n2 // 2))
     assert e.value.status == scpd.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_raw_kernel_configurations(scpd, fmt):
+    """Everything the reference can be configured to outside the in-range datapaths (decode_raw.cuh): LLR_BITS 5
+    (the +-31 alphabet wraps modulo 32 on the sc_fifo<LLR> write), SIGMAG for arbitrary (LLR_BITS, PAR, EXTENDED),
+    N below 128, un-saturated leaves wider than 16 bits, the whole int8 input range."""
+    import torch
+    rng = np.random.default_rng(50 + fmt)
+    for key, nfr in (("c1", 300), ("c2", 60)):
+        name, n, k, snr = CONFIG_SETS[key]
+        flags = scpd.packed_flags(name, n)
+        llr = _llrs(31 + fmt, n, nfr, k, snr).copy()
+        llr[-1] = 0
+        llr[-2] = rng.integers(-128, 128, n).astype(np.int8)
+        cases = [(16, 5, 1), (16, 5, 0), (64, 5, 1), (256, 9, 1), (1, 5, 1)]
+        if fmt == 1:
+            cases += [(4, 9, 1), (256, 8, 1), (1, 6, 1), (2, 8, 0), (16, 9, 0), (16, 7, 0)]
+        for par, q, ext in cases:
+            for prune in (0, 2):
+                dec = scpd.Decoder(n, k, flags, par=par, llr_bits=q, fmt=fmt, extended=ext, pruning=prune)
+                assert "raw" in dec.kernel_name, (par, q, ext, dec.kernel_name)
+                want = _oracle(n, par, q, ext, flags, llr, fmt)
+                got = dec.decode(torch.from_numpy(llr).cuda()).cpu().numpy().view(np.uint32)
+                assert (got == want).all(), (key, par, q, ext, prune)
+                dec.close()
+    for n in (4, 8, 32, 64):  # below the bit-sliced kernel's smallest tree
+        for trial in range(3):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-128, 128, size=(70, n)).astype(np.int8)
+            for par, q in ((1, 6), (2, 5), (2, 8), (16, 6), (32, 9)):
+                if 2 * par > n or (fmt == 0 and q > 5):
+                    continue
+                dec = scpd.Decoder(n, int(flags.sum()), flags, par=par, llr_bits=q, fmt=fmt, pruning=trial)
+                assert "raw" in dec.kernel_name
+                assert (dec.decode_host(llr) == ol.decode_packed(n, par, q, fmt, 1, flags, llr)).all(), (n, par, q, trial)
+                dec.close()
+    if fmt == 1:  # mis-aligned LLR buffer: the bit-sliced SIGMAG handle falls back to the raw-pattern kernel
+        name, n, k, snr = CONFIG_SETS["c1"]
+        flags = scpd.packed_flags(name, n)
+        llr = _llrs(9, n, 100, k, snr)
+        dec = scpd.Decoder(n, k, flags, llr_bits=6, fmt=1)
+        assert "bit-sliced" in dec.kernel_name
+        buf = torch.zeros(llr.size + 1, dtype=torch.int8, device="cuda")
+        buf[1:] = torch.from_numpy(llr).cuda().flatten()
+        got = dec.decode(buf[1:].view(100, n)).cpu().numpy().view(np.uint32)
+        assert (got == ol.decode_packed(n, 16, 6, 1, 1, flags, llr)).all()
 
 
 def test_c1_headline_many_frames(scpd):

@@ -148,3 +148,38 @@ def test_c_abi_argument_validation_without_gpu():
     assert abs(scpd.sigma(2.5, 0.5) - ol.sigma(2.5, 0.5)) < 1e-7
     assert scpd.lib.scpd_status_string(scpd.E_IO) == b"i/o error"
     assert scpd.lib.scpd_decode(None, None, 1, None, None) == scpd.E_ARG
+
+
+def _remu(fmt, g, flags, n, par, q, ext, prune, llr, ls=-1, beta_sm=1, warps=1, grid=1):
+    out = np.zeros((len(llr), max(n // 32, 1)), np.uint32)
+    rc = _emu_lib('libwarp_emu.so').emu_raw_decode(fmt, g, int(np.log2(n)), int(np.log2(par)), q, ext, prune, ol.P(flags),
+                                                   ol.P(llr), ctypes.c_size_t(len(llr)), ol.P(out), ls, beta_sm, warps, grid)
+    assert rc == 0, rc
+    return out
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("q", [5, 6, 8, 9])
+def test_raw_kernel_source_under_warp_emulator(fmt, q):
+    """decode_raw.cuh (the every-configuration kernel) executed lane by lane on the CPU against the oracle:
+    both formats, LLR_BITS 5 (the +-31 alphabet wraps) ... 9, PAR 1 ... 256, EXTENDED 0/1, N 8 ... 1024, the whole int8
+    input range (wrap-around on the sc_fifo<LLR> write), storage split between shared memory and workspace."""
+    rng = np.random.default_rng(100 * fmt + q)
+    for n, par, ext, g in [(8, 2, 1, 8), (8, 4, 1, 32), (16, 1, 1, 8), (64, 16, 0, 8), (64, 32, 1, 32), (256, 16, 1, 8),
+                           (512, 256, 1, 32), (1024, 64, 0, 8)]:
+        k = n // 2
+        flags = np.zeros(n, np.uint8)
+        flags[rng.permutation(n)[:k]] = 1
+        if n == 1024:
+            flags = scpd.packed_flags("FB_N1024_K512", n)
+        nfr = 32 // g + 2
+        llr = rng.integers(-31, 32, (nfr, n)).astype(np.int8)
+        llr[0] = 0
+        llr[1] = rng.integers(-128, 128, n).astype(np.int8)  # out of range for every LLR_BITS here
+        want = ol.decode_packed(n, par, q, fmt, ext, flags, llr)
+        for prune in ((0, 2) if n <= 64 else (2,)):
+            got = _remu(fmt, g, flags, n, par, q, ext, prune, llr)
+            assert (got == want).all(), (n, par, ext, g, prune)
+        if n == 256:
+            got = _remu(fmt, g, flags, n, par, q, ext, 1, llr, ls=4, beta_sm=0, warps=2, grid=2)
+            assert (got == want).all(), (n, par, ext, g, "workspace")
