@@ -10,7 +10,9 @@
  * Conventions kept from the reference:
  *   - LLRs: one signed 8-bit value per code bit, natural index order, positive <=> bit 0
  *     (sc_bpsk.h:53), produced by the quantiser clamp(trunc(4y), -31, 31) (sc_quantizer.h:77-80);
- *     any value in [-(2^(Q-1)-1), 2^(Q-1)-1] is accepted (Q = llr_bits).
+ *     any value in [-(2^(Q-1)-1), 2^(Q-1)-1] is accepted (Q = llr_bits).  With llr_bits = 5 the
+ *     alphabet does not fit and the reference truncates it to 5 bits on the sc_fifo<LLR> write
+ *     (wrapper_in.h:33-34); that configuration reproduces the truncation for any int8 input.
  *   - frozen table: N flags, 1 = information bit, 0 = frozen (Writer.h:86-93; my_module.h:92-95).
  *   - output: the estimated CODEWORD x^ (what my_module streams out of bit_mem_1,
  *     my_module.h:1859-1866), packed LSB-first: bit i of a frame is bit (i % 32) of word i / 32
@@ -38,7 +40,7 @@ typedef enum {
     SCPD_OK = 0,
     SCPD_E_ARG = 1,         /* null pointer / bad size */
     SCPD_E_CONFIG = 2,      /* N not a power of two, 2*PAR > N, K != popcount(flags), ... */
-    SCPD_E_UNSUPPORTED = 3, /* valid reference configuration this build has no kernel for */
+    SCPD_E_UNSUPPORTED = 3, /* beyond the kernels: n above 2^20 or par above 512 */
     SCPD_E_IO = 4,          /* file missing / unparsable */
     SCPD_E_CUDA = 5,        /* CUDA runtime error (scpd_last_error() has the text) */
     SCPD_E_NOMEM = 6
@@ -95,7 +97,10 @@ void scpd_destroy(scpd_decoder* dec);
  * d_llr  : [nframes][n] int8, device.      d_xhat : [nframes][n/32] uint32, device.
  * Large batches run on the bit-sliced kernel (32 frames per register bit; the handle then keeps a
  * bit-plane copy of the batch, nframes * n bytes, plus a workspace for the resident frame groups); batches
- * too small to fill the GPU that way run on the int16x2 kernel.  Results are identical either way. */
+ * too small to fill the GPU that way run on the int16x2 kernel.  Results are identical either way.
+ * Configurations outside those two datapaths (llr_bits 5, SIGMAG combinations without a bit-sliced
+ * instantiation, n < 128 in SIGMAG, EXTENDED leaves wider than 16 bits) run on the raw-pattern kernel,
+ * which models the reference's W-bit wrap-around exactly and is slower. */
 int scpd_decode(scpd_decoder* dec, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat,
                 void* cuda_stream);
 /* Same through host buffers (pinned or pageable): the batch is cut into chunks that flow through an
