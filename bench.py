@@ -338,8 +338,7 @@ def main():
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         ge.build()
     else:  # other local ranks wait for rank 0's build instead of racing nvcc
-        from sc_polar_decoder_hls_b200.build import wait_for_lib
-        wait_for_lib()
+        ge.build_module().wait_for_lib()
     if a.impl == "reference":
         run_reference_arm(a)
     else:

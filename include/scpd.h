@@ -123,6 +123,20 @@ int scpd_kernel_timing(scpd_decoder* dec, int enable);
 int scpd_last_kernel_ms(scpd_decoder* dec, float* ms);
 /* Which kernel family and layout this handle launches (static text, valid until the next call). */
 const char* scpd_kernel_name(const scpd_decoder* dec);
+/* The function x level matrix of sc_monitor (src/rtl_simu_testbench/sc_monitor/sc_monitor.h:50-441), from
+ * the frozen table alone (host only, no device needed): per FSM function and node size 2^l, the node visits
+ * per frame and the trip counts of the reference's pipelined loops (f_loop / g_loop / h_loop,
+ * my_module.h:373,704,903: half the node's PAR-wide words; one per leaf decode R, :592-595).  With
+ * SCPD_PRUNE_NONE this is the reference at PRUNING_LEVEL 0 and total_iterations its loop cycles per frame;
+ * with pruning it is the walk this library executes (R0 / R1: nodes skipped / decided by hard decision). */
+enum { SCPD_STAGE_F = 0, SCPD_STAGE_G = 1, SCPD_STAGE_H = 2, SCPD_STAGE_R = 3, SCPD_STAGE_R0 = 4,
+       SCPD_STAGE_R1 = 5, SCPD_STAGE_FUNCS = 6 };
+typedef struct {
+    uint64_t visits[SCPD_STAGE_FUNCS][32];     /* [function][l]: node visits per frame            */
+    uint64_t iterations[SCPD_STAGE_FUNCS][32]; /* [function][l]: loop iterations (PAR-wide words) */
+    uint64_t total_iterations;
+} scpd_stage_matrix;
+int scpd_stage_profile(const scpd_config* cfg, const uint8_t* h_info_flags, scpd_stage_matrix* out);
 
 /* ---- testbench harness on the device: src/testbench/ ---- */
 /* sigma = 1/sqrt(2 R 10^(EbN0/10)), main.cpp:91-98 (the reference hard-codes R = 0.5). */

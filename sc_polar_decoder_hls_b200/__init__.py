@@ -26,6 +26,15 @@ class Config(ctypes.Structure):
                 ("n", "k", "par", "llr_bits", "format", "extended", "pruning", "reserved")]
 
 
+class StageMatrix(ctypes.Structure):
+    """scpd_stage_matrix: [function][level] node visits and loop iterations per frame."""
+    _fields_ = [("visits", (ctypes.c_uint64 * 32) * 6), ("iterations", (ctypes.c_uint64 * 32) * 6),
+                ("total_iterations", ctypes.c_uint64)]
+
+
+STAGE_FUNCS = ("F", "G", "H", "R", "R0", "R1")
+
+
 class ScpdError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(f"scpd status {status}: {msg}")
@@ -56,6 +65,7 @@ def _load():
         "scpd_kernel_timing": (c.c_int, [vp, c.c_int]),
         "scpd_last_kernel_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "scpd_kernel_name": (c.c_char_p, [vp]),
+        "scpd_stage_profile": (c.c_int, [c.POINTER(Config), u8p, c.POINTER(StageMatrix)]),
         "scpd_sigma": (c.c_float, [c.c_float, c.c_float]),
         "scpd_channel_generate": (c.c_int, [c.c_uint32, c.c_uint64, c.c_size_t, c.c_uint8, c.c_float, vp,
                                             c.c_int, vp, vp]),
@@ -77,7 +87,7 @@ EXPORTS = ["scpd_frozen_load_order", "scpd_frozen_load_flags", "scpd_frozen_writ
            "scpd_frozen_write_flags", "scpd_write_polar_parameters", "scpd_create", "scpd_destroy",
            "scpd_decode", "scpd_decode_host", "scpd_extract_info", "scpd_get_config",
            "scpd_schedule_stats", "scpd_launch_count", "scpd_kernel_timing", "scpd_last_kernel_ms",
-           "scpd_kernel_name", "scpd_sigma", "scpd_channel_generate",
+           "scpd_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate",
            "scpd_count_errors", "scpd_run_ber", "scpd_last_error", "scpd_status_string"]
 
 
@@ -129,6 +139,17 @@ def packed_flags(name, n):
 
 def sigma(ebn0_db, rate):
     return float(lib.scpd_sigma(ebn0_db, rate))
+
+
+def stage_profile(n, k, flags, par=16, pruning=PRUNE_NONE):
+    """The function x level matrix of the reference's sc_monitor (sc_monitor.h:50-441) from the frozen table:
+    returns (visits, iterations, total) with visits / iterations numpy [6, 32] indexed [STAGE_FUNCS, log2 node size]."""
+    flags = np.ascontiguousarray(flags, np.uint8)
+    cfg = Config(n, k, par, 8, FMT_CA2, 1, pruning, 0)
+    m = StageMatrix()
+    check(lib.scpd_stage_profile(ctypes.byref(cfg), _np_ptr(flags), ctypes.byref(m)))
+    return (np.array(m.visits, np.uint64).reshape(6, 32), np.array(m.iterations, np.uint64).reshape(6, 32),
+            int(m.total_iterations))
 
 
 # ------------------------------------------------------------------ decoder handle

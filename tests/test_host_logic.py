@@ -183,3 +183,54 @@ def test_raw_kernel_source_under_warp_emulator(fmt, q):
         if n == 256:
             got = _remu(fmt, g, flags, n, par, q, ext, 1, llr, ls=4, beta_sm=0, warps=2, grid=2)
             assert (got == want).all(), (n, par, ext, g, "workspace")
+
+
+def test_stage_profile_matches_reference_fsm_trip_counts():
+    """scpd_stage_profile (host only): at PRUNE_NONE the matrix is the reference FSM at PRUNING_LEVEL 0 -- every node
+    above the leaf runs f_loop, g_loop and h_loop for half its PAR-wide words (my_module.h:343,373,704,903) and every
+    leaf is one R visit -- and with pruning it follows an independent recursion over the frozen table."""
+    n, k, par = 1024, 512, 16
+    flags = scpd.packed_flags("FB_N1024_K512", n)
+    vis, it, total = scpd.stage_profile(n, k, flags, par=par, pruning=scpd.PRUNE_NONE)
+    F, G, H, R, R0, R1 = range(6)
+    for l in range(5, 11):
+        nodes, words = n >> l, (1 << l) // par
+        for fn in (F, G, H):
+            assert vis[fn][l] == nodes and it[fn][l] == nodes * words // 2
+    assert vis[R][4] == n // par and vis[R0].sum() == 0 and vis[R1].sum() == 0
+    assert total == 3 * 6 * (n // par) // 2 + n // par
+
+    def rec(l, o, prune, acc):
+        size = 1 << l
+        c = int(flags[o:o + size].sum())
+        if prune >= 1 and c == 0:
+            acc["R0"] += 1
+            return
+        if size <= par:
+            acc["R"] += 1
+            return
+        if prune >= 2 and c == size:
+            acc["R1"] += 1
+            return
+        h = size // 2
+        if prune >= 1 and flags[o:o + h].sum() == 0:
+            acc["R0"] += 1
+        else:
+            acc["F"] += 1
+            rec(l - 1, o, prune, acc)
+        if prune >= 1 and flags[o:o + h].sum() != 0 and flags[o + h:o + size].sum() == 0:
+            acc["R0"] += 1
+        else:
+            acc["G"] += 1
+            rec(l - 1, o + h, prune, acc)
+        acc["H"] += 1
+
+    for prune in (1, 2):
+        acc = dict.fromkeys(scpd.STAGE_FUNCS, 0)
+        rec(10, 0, prune, acc)
+        vis, it, total2 = scpd.stage_profile(n, k, flags, par=par, pruning=prune)
+        assert {f: int(vis[i].sum()) for i, f in enumerate(scpd.STAGE_FUNCS)} == acc
+        assert total2 < total
+    rnd = np.random.default_rng(0)
+    bad = scpd.Config(48, 1, 16, 8, 0, 1, 0, 0)
+    assert scpd.lib.scpd_stage_profile(ctypes.byref(bad), ol.P(flags), ctypes.byref(scpd.StageMatrix())) == scpd.E_CONFIG

@@ -5,6 +5,7 @@
 //   ber_bench --order FILE | --flags FILE  -n N -k K [--par 16] [--q 8] [--sm] [--no-ext]
 //             [--prune 0|1|2] [--snr 2.5[:step:stop]] [--rate R] [--frames F] [--seed 0xF0] [--device D]
 //             [--gpus G]   (frames split over G devices as independent streams; counters summed)
+//             [--monitor]  (print the function x level matrix of sc_monitor.h for this table and exit; no GPU needed)
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -22,6 +23,7 @@ int main(int argc, char** argv) {
     double snr0 = 2.5, snr_step = 0.0, snr1 = 2.5, rate = -1.0;
     uint64_t frames = 1 << 16;
     int seed = 0xF0, device = 0, gpus = 1;
+    bool monitor = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -39,6 +41,7 @@ int main(int argc, char** argv) {
         else if (a == "--seed") seed = (int)std::strtol(next(), nullptr, 0);
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--gpus") gpus = std::atoi(next());
+        else if (a == "--monitor") monitor = true;
         else if (a == "--snr") {
             double v[3] = {2.5, 0, 0};
             int c = std::sscanf(next(), "%lf:%lf:%lf", &v[0], &v[1], &v[2]);
@@ -58,6 +61,24 @@ int main(int argc, char** argv) {
         std::vector<uint8_t> flags = order.empty() ? scpd::load_flag_table(flagsf, n, &k) : scpd::load_order_table(order, n, k);
         if (rate <= 0) rate = double(k) / double(n);  // the reference hard-codes R = 0.5 (main.cpp:92)
         scpd_config cfg{n, k, par, q, fmt, ext, prune, 0};
+        if (monitor) {  // layout of sc_monitor.h:170-190 ("Matrix Level / Function"), loop iterations per frame
+            scpd_stage_matrix m;
+            if (scpd_stage_profile(&cfg, flags.data(), &m) != SCPD_OK) throw std::runtime_error("bad configuration");
+            int top = 0;
+            while ((1u << top) < n) top++;
+            static const char* names[SCPD_STAGE_FUNCS] = {"F", "G", "H", "R", "R_R0", "R_R1"};
+            std::printf("[MONITOR] loop iterations per frame : %llu (pruning %u)\n", (unsigned long long)m.total_iterations, prune);
+            std::printf("  Level     |");
+            for (int l = top; l >= 0; l--) std::printf("%8u", 1u << l);
+            std::printf("\n");
+            for (int f = 0; f < SCPD_STAGE_FUNCS; f++) {
+                std::printf("  fct %-5s |", names[f]);
+                for (int l = top; l >= 0; l--)
+                    std::printf("%8llu", (unsigned long long)(f >= SCPD_STAGE_R0 ? m.visits[f][l] : m.iterations[f][l]));
+                std::printf("\n");
+            }
+            return 0;
+        }
         std::printf("(II) Frame size %u, K %u, LLR width %u, QUANT [4, -31, 31], PAR %u, %s, EXTENDED %u, %d GPU(s)\n", n, k,
                     q, par, fmt == SCPD_FMT_CA2 ? "CA2" : "SIGMAG", ext, gpus);
         for (double snr = snr0; snr <= snr1 + 1e-9; snr += (snr_step > 0 ? snr_step : 1e9)) {
