@@ -97,6 +97,16 @@ static int jump_table_device(int device, XsJumpTable* out) {
 
 using namespace scpd;
 
+struct FastPlan {
+    int group = 0, warps = 4, log2s = 0, ctas_per_sm = 1;
+    std::vector<uint32_t> sched_host;
+    ScheduleStats stats;
+    uint32_t* d_sched = nullptr;
+    uint32_t lsa = 0, lsb = 0, sm_alpha_cells = 0, sm_stride = 0;
+    size_t smem_bytes = 0;
+    unsigned long long ws_stride = 0;
+};
+
 struct scpd_decoder {
     scpd_config cfg;
     int device = 0;
@@ -114,17 +124,11 @@ struct scpd_decoder {
     int ctas_per_sm = 1, num_sms = 1;
     uint32_t* d_ws = nullptr;
     size_t ws_bytes = 0;
-    // fast-kernel plan (decode_fast.cuh); fast_group == 0: not available for this configuration
-    int fast_group = 0;
-    int fast_warps = 4;
-    int fast_log2s = 0;
-    std::vector<uint32_t> fast_sched_host;
-    ScheduleStats fast_stats;
-    uint32_t* d_fast_sched = nullptr;
-    uint32_t fast_lsa = 0, fast_lsb = 0, fast_sm_alpha_cells = 0, fast_sm_stride = 0;
-    size_t fast_smem_bytes = 0;
-    unsigned long long fast_ws_stride = 0;
-    int fast_ctas_per_sm = 1;
+    // fast-kernel plans (decode_fast.cuh); fast.group == 0: not available for this configuration.
+    // fast_wide: the same kernel with wider lane groups (16, 32 lanes per frame pair), for batches too small to
+    // fill the GPU with the default group width
+    FastPlan fast;
+    std::vector<FastPlan> fast_wide;
     uint8_t* d_fast_ws = nullptr;
     size_t fast_ws_bytes = 0;
     // bit-sliced kernel plan (decode_bs.cuh); bs_ok == false: not available for this configuration
@@ -186,6 +190,7 @@ static fast_kernel_t fast_kernel_ptr(int group, int log2par, int ext) {
             case 4: return sc_decode_fast_kernel<4, 4, true>;
             case 8: return sc_decode_fast_kernel<8, 4, true>;
             case 16: return sc_decode_fast_kernel<16, 4, true>;
+            case 32: return sc_decode_fast_kernel<32, 4, true>;
             default: return nullptr;
         }
     }
@@ -290,27 +295,20 @@ static int plan_bs(scpd_decoder* d, const uint8_t* flags) {
     return SCPD_OK;
 }
 
-// Decide whether the fast kernel applies and size its shared-memory / workspace layout.
-static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
-    d->fast_group = 0;
-    const char* ksel = std::getenv("SCPD_KERNEL");
-    if (ksel && std::strcmp(ksel, "generic") == 0) return SCPD_OK;
-    if (d->cfg.format != SCPD_FMT_CA2 || d->cfg.llr_bits > 8 || d->log2par < 1) return SCPD_OK;
-    int g = env_int("SCPD_GROUP", 8);
+// Size the shared-memory / workspace layout of the fast kernel with g lanes per frame pair.  fp->group stays 0
+// when the kernel does not apply to this configuration.
+static int plan_fast_g(scpd_decoder* d, const uint8_t* flags, int g, FastPlan* fp) {
+    fp->group = 0;
     fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
-    if (!k) {
-        g = 8;
-        k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
-    }
     if (!k) return SCPD_OK;
     const int log2s = ilog2(8 * g);
     if (d->log2par > log2s || d->log2n < log2s + 1 || d->cfg.n < 32) return SCPD_OK;  // leaf must sit inside the register subtree
-    d->fast_log2s = log2s;
-    d->fast_sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning, flags,
-                                        &d->fast_stats, log2s);
-    d->fast_warps = std::max(1, std::min(8, env_int("SCPD_WARPS", 8)));
+    fp->log2s = log2s;
+    fp->sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning, flags,
+                                    &fp->stats, log2s);
+    fp->warps = std::max(1, std::min(8, env_int("SCPD_WARPS", 8)));
     const int gpw = 32 / g;
-    const int fp_per_cta = d->fast_warps * gpw;
+    const int fp_per_cta = fp->warps * gpw;
     const size_t budget = (size_t)env_int("SCPD_SMEM_KB", 100) * 1024;
     const size_t per_fp = budget / fp_per_cta;
     const uint32_t n = d->cfg.n;
@@ -336,24 +334,53 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
         const int pad = env_int("SCPD_BANK_PAD", g < 8 ? 16 * g : 32);
         stride += (size_t)pad;
     }
-    d->fast_lsa = (uint32_t)lsa;
-    d->fast_lsb = (uint32_t)lsb;
-    d->fast_sm_alpha_cells = (uint32_t)(2u << lsa);
-    d->fast_sm_stride = (uint32_t)stride;
-    d->fast_smem_bytes = stride * fp_per_cta;
-    d->fast_ws_stride = ((unsigned long long)n * 5ull + 255ull) & ~255ull;  // alpha 4n bytes + partial sums n bytes
-    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->fast_smem_bytes));
+    fp->lsa = (uint32_t)lsa;
+    fp->lsb = (uint32_t)lsb;
+    fp->sm_alpha_cells = (uint32_t)(2u << lsa);
+    fp->sm_stride = (uint32_t)stride;
+    fp->smem_bytes = stride * fp_per_cta;
+    fp->ws_stride = ((unsigned long long)n * 5ull + 255ull) & ~255ull;  // alpha 4n bytes + partial sums n bytes
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, d->fast_warps * 32,
-                                                           d->fast_smem_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, fp->warps * 32, fp->smem_bytes));
     if (occ < 1) return SCPD_OK;  // does not fit: stay on the generic kernel
-    d->fast_ctas_per_sm = occ;
-    d->fast_group = g;
+    fp->ctas_per_sm = occ;
+    fp->group = g;
     if (env_int("SCPD_VERBOSE", 0))
         fprintf(stderr, "[scpd] fast kernel G=%d warps/CTA=%d: alpha levels <=%d and partial sums <=%d in smem, "
-                "%zu B/pair, %zu B/CTA, %d CTAs/SM, workspace %llu B/pair\n", g, d->fast_warps, lsa, lsb, stride,
-                d->fast_smem_bytes, occ, d->fast_ws_stride);
+                "%zu B/pair, %zu B/CTA, %d CTAs/SM, workspace %llu B/pair\n", g, fp->warps, lsa, lsb, stride,
+                fp->smem_bytes, occ, fp->ws_stride);
     return SCPD_OK;
+}
+
+// Decide whether the fast kernel applies; default 8 lanes per frame pair, plus the wider groups for small batches.
+static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
+    d->fast.group = 0;
+    d->fast_wide.clear();
+    const char* ksel = std::getenv("SCPD_KERNEL");
+    if (ksel && std::strcmp(ksel, "generic") == 0) return SCPD_OK;
+    if (d->cfg.format != SCPD_FMT_CA2 || d->cfg.llr_bits > 8 || d->log2par < 1) return SCPD_OK;
+    const bool pinned_group = std::getenv("SCPD_GROUP") != nullptr;
+    int rc = plan_fast_g(d, flags, env_int("SCPD_GROUP", 8), &d->fast);
+    if (rc == SCPD_OK && !d->fast.group) rc = plan_fast_g(d, flags, 8, &d->fast);
+    if (rc != SCPD_OK || !d->fast.group || pinned_group) return rc;
+    for (int g = 2 * d->fast.group; g <= 32; g *= 2) {
+        FastPlan w;
+        rc = plan_fast_g(d, flags, g, &w);
+        if (rc != SCPD_OK) return rc;
+        if (w.group) d->fast_wide.push_back(std::move(w));
+    }
+    return SCPD_OK;
+}
+
+// The lane-group width for a batch of num_fp frame pairs: widen the group while the batch leaves most of the
+// GPU's lanes idle (measured, profiles/tuning_r1.md: N = 2^19, 1024 frames: 5.8 / 11.0 Gb/s with 8 / 16 lanes).
+static const FastPlan& pick_fast(const scpd_decoder* d, unsigned long long num_fp) {
+    const FastPlan* best = &d->fast;
+    const unsigned long long lanes_wanted = (unsigned long long)d->num_sms * (unsigned)env_int("SCPD_FAST_WIDE_LANES", 256);
+    for (const FastPlan& w : d->fast_wide)
+        if (num_fp * (unsigned)best->group < lanes_wanted) best = &w;
+    return *best;
 }
 
 static const void* raw_kernel_ptr(int group) {
@@ -496,12 +523,15 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     if (e == cudaSuccess)
         e = cudaMemcpy(d->d_sched, d->sched_host.data(), d->sched_host.size() * sizeof(uint32_t),
                        cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && d->fast_group) {
-        e = cudaMalloc(&d->d_fast_sched, d->fast_sched_host.size() * sizeof(uint32_t));
+    auto upload_fast = [&](FastPlan& fp) {
+        if (e != cudaSuccess || !fp.group) return;
+        e = cudaMalloc(&fp.d_sched, fp.sched_host.size() * sizeof(uint32_t));
         if (e == cudaSuccess)
-            e = cudaMemcpy(d->d_fast_sched, d->fast_sched_host.data(), d->fast_sched_host.size() * sizeof(uint32_t),
+            e = cudaMemcpy(fp.d_sched, fp.sched_host.data(), fp.sched_host.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice);
-    }
+    };
+    upload_fast(d->fast);
+    for (FastPlan& w : d->fast_wide) upload_fast(w);
     if (e == cudaSuccess && d->raw_ok) {
         e = cudaMalloc(&d->d_raw_sched, d->raw_sched_host.size() * sizeof(uint32_t));
         if (e == cudaSuccess)
@@ -528,7 +558,8 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaSetDevice(d->device);
     cudaFree(d->d_sched);
     cudaFree(d->d_ws);
-    cudaFree(d->d_fast_sched);
+    cudaFree(d->fast.d_sched);
+    for (FastPlan& w : d->fast_wide) cudaFree(w.d_sched);
     cudaFree(d->d_fast_ws);
     cudaFree(d->d_bs_sched);
     cudaFree(d->d_bs_ws);
@@ -554,13 +585,14 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
 }
 
 static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
-    const int g = d->fast_group, gpw = 32 / g;
-    const unsigned long long fp_per_cta = (unsigned long long)d->fast_warps * gpw;
     const unsigned long long num_fp = (nframes + 1) / 2;
+    const FastPlan& fp = pick_fast(d, num_fp);
+    const int g = fp.group, gpw = 32 / g;
+    const unsigned long long fp_per_cta = (unsigned long long)fp.warps * gpw;
     unsigned long long grid = (num_fp + fp_per_cta - 1) / fp_per_cta;
-    const unsigned long long max_grid = (unsigned long long)d->num_sms * d->fast_ctas_per_sm;
+    const unsigned long long max_grid = (unsigned long long)d->num_sms * fp.ctas_per_sm;
     if (grid > max_grid) grid = max_grid;
-    const size_t ws_need = (size_t)(grid * fp_per_cta * d->fast_ws_stride);
+    const size_t ws_need = (size_t)(grid * fp_per_cta * fp.ws_stride);
     if (ws_need > d->fast_ws_bytes) {
         CUDA_TRY(cudaStreamSynchronize(st));
         cudaFree(d->d_fast_ws);
@@ -570,7 +602,7 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
         d->fast_ws_bytes = ws_need;
     }
     FastParams p;
-    p.sched = d->d_fast_sched;
+    p.sched = fp.d_sched;
     p.llr = d_llr;
     p.xhat = d_xhat;
     p.nframes = nframes;
@@ -579,15 +611,15 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     p.log2n = (uint32_t)d->log2n;
     p.wpf = d->wpf;
     p.satv = (1u << (d->cfg.llr_bits - 1)) - 1u;
-    p.lsa = d->fast_lsa;
-    p.lsb = d->fast_lsb;
-    p.sm_alpha_cells = d->fast_sm_alpha_cells;
-    p.sm_stride = d->fast_sm_stride;
+    p.lsa = fp.lsa;
+    p.lsb = fp.lsb;
+    p.sm_alpha_cells = fp.sm_alpha_cells;
+    p.sm_stride = fp.sm_stride;
     p.ws = d->d_fast_ws;
-    p.ws_stride = d->fast_ws_stride;
+    p.ws_stride = fp.ws_stride;
     fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
-    k<<<dim3((unsigned)grid), dim3((unsigned)(d->fast_warps * 32)), d->fast_smem_bytes, st>>>(p);
+    k<<<dim3((unsigned)grid), dim3((unsigned)(fp.warps * 32)), fp.smem_bytes, st>>>(p);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -709,15 +741,17 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     cudaStream_t st = (cudaStream_t)stream;
     if (d->raw_only) return decode_raw(d, d_llr, nframes, d_xhat, st);
     // One warp walks the tree of a 32-frame group alone, so the bit-sliced kernel needs many groups to fill the
-    // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 16 k at N = 4096
-    // and 32768, far fewer for the largest trees) the int16x2 kernel with 2 frames per lane group is faster.
-    const unsigned long long bs_min_groups = d->log2n <= 11 ? 1536 : d->log2n <= 15 ? 512 : d->log2n <= 17 ? 128 : 64;
-    const bool bs_small = d->fast_group && d->cfg.format == SCPD_FMT_CA2 && !d->kernel_pinned &&
+    // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 24 k at N = 4096,
+    // 16 k at N = 32768 and 131072, 8 k at N = 2^19) the int16x2 kernel is faster: 2 frames per lane group, and
+    // lane groups that widen to 16 / 32 lanes as the batch shrinks (pick_fast).
+    const unsigned long long bs_min_groups = (unsigned long long)env_int(
+        "SCPD_BS_MIN_GROUPS", d->log2n <= 11 ? 1536 : d->log2n <= 13 ? 768 : d->log2n <= 17 ? 512 : 256);
+    const bool bs_small = d->fast.group && d->cfg.format == SCPD_FMT_CA2 && !d->kernel_pinned &&
                           (nframes + 31) / 32 < bs_min_groups;
     if (d->bs_ok && !bs_small && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0)
         return decode_bs(d, d_llr, nframes, d_xhat, st);
     if (d->cfg.format != SCPD_FMT_CA2) return decode_raw(d, d_llr, nframes, d_xhat, st);  // mis-aligned LLR buffer
-    if (d->fast_group && (reinterpret_cast<uintptr_t>(d_llr) & 7u) == 0) return decode_fast(d, d_llr, nframes, d_xhat, st);
+    if (d->fast.group && (reinterpret_cast<uintptr_t>(d_llr) & 7u) == 0) return decode_fast(d, d_llr, nframes, d_xhat, st);
     const int gpw = 32 / d->group;
     const unsigned long long fp_per_cta = (unsigned long long)d->warps_per_cta * gpw;
     const unsigned long long num_fp = (nframes + 1) / 2;
@@ -867,8 +901,8 @@ extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
     else if (d->bs_ok)
         snprintf(buf, sizeof buf, "sc_decode_bs_kernel (bit-sliced, %d lanes per 32-frame group, %d warps/CTA)", d->bs_group,
                  d->bs_warps);
-    else if (d->fast_group)
-        snprintf(buf, sizeof buf, "sc_decode_fast_kernel (int16x2, %d lanes per frame pair)", d->fast_group);
+    else if (d->fast.group)
+        snprintf(buf, sizeof buf, "sc_decode_fast_kernel (int16x2, %d lanes per frame pair)", d->fast.group);
     else
         snprintf(buf, sizeof buf, "sc_decode_generic_kernel (int16x2, %d lanes per frame pair)", d->group);
     return buf;
@@ -894,7 +928,7 @@ extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
 }
 extern "C" int scpd_schedule_stats(const scpd_decoder* d, uint64_t* n_ops, uint64_t* n_fg) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_schedule_stats: null decoder");
-    const ScheduleStats& st = d->raw_only ? d->raw_stats : d->bs_ok ? d->bs_stats : d->fast_group ? d->fast_stats : d->stats;
+    const ScheduleStats& st = d->raw_only ? d->raw_stats : d->bs_ok ? d->bs_stats : d->fast.group ? d->fast.stats : d->stats;
     if (n_ops) *n_ops = st.n_ops;
     if (n_fg) *n_fg = st.n_f + st.n_g;
     return SCPD_OK;

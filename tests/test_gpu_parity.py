@@ -64,7 +64,7 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
     dec.close()
 
 
-@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "bs8", "bs16", "bs32", "bs32ws"])
+@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "bs8", "bs16", "bs32", "bs32ws"])
 def kernel_mode(request, monkeypatch):
     """Selects the decode kernel through the library's environment switches (read in scpd_create):
     the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
