@@ -433,18 +433,24 @@ __device__ __noinline__ uint2 node8_rt_l2(uint32_t a0, uint32_t a1, uint32_t sub
     return make_uint2(b[0], b[1]);
 }
 
-template <int G, int LOG2PAR, bool EXT>
+// W > 1 (with G = 32): W warps -- the whole CTA -- walk ONE frame pair together.  Nodes above the register
+// subtree are spread over all G * W lanes with a CTA barrier behind every op; the subtree itself is walked by
+// warp 0.  For batches too small to fill the GPU with one warp per pair (large trees).
+template <int G, int LOG2PAR, bool EXT, int W = 1>
 struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
     using LeafCtx<G, LOG2PAR, EXT>::gl;
     using LeafCtx<G, LOG2PAR, EXT>::satp;
     using LeafCtx<G, LOG2PAR, EXT>::satn;
     static constexpr unsigned FULL = 0xFFFFFFFFu;
+    static constexpr int GX = G * W;  // lanes that share the nodes above the register subtree
     static constexpr int S = 8 * G;
     static constexpr int LOG2S = (G == 1) ? 3 : (G == 2) ? 4 : (G == 4) ? 5 : (G == 8) ? 6 : (G == 16) ? 7 : 8;
     static constexpr int DESC_WORDS = (2 * (S - 1) + 31) / 32;
     static constexpr int FLAG_WORDS = (S + 31) / 32;
 
     const FastParams& p;
+    int gx;         // lane index among the GX lanes of the frame pair (= gl when W == 1)
+    bool sub_warp;  // this warp walks the register subtrees
     uint32_t sm_alpha_a, sm_beta_a;  // shared-window byte addresses
     uint8_t* sm_alpha_p;             // generic pointers to the same regions (register subtree I/O)
     uint8_t* sm_beta_p;
@@ -458,6 +464,12 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
     uint32_t flagw[FLAG_WORDS];  // raw information flags of the current subtree
 
     __device__ FastDecoder(const FastParams& p_) : p(p_) {}
+    __device__ __forceinline__ void bar() const {
+        if constexpr (W == 1)
+            __syncwarp();
+        else
+            __syncthreads();
+    }
 
     // ------------------------------------------------------------ storage
     template <bool SM>
@@ -513,9 +525,9 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
         const uint32_t h = 1u << (l - 1);
         const MemRef<ASM> src = aref<ASM>(l);
         const MemRef<DSM> dst = aref<DSM>(l - 1);
-        uint32_t e = 8u * gl;
-        for (; e + 8u * G < h; e += 16u * G) {
-            const uint32_t e1 = e + 8u * G;
+        uint32_t e = 8u * gx;
+        for (; e + 8u * GX < h; e += 16u * GX) {
+            const uint32_t e1 = e + 8u * GX;
             const uint4 a0 = ROOT ? root8(e) : src.ld128(2 * e), b0 = ROOT ? root8(e + h) : src.ld128(2 * (e + h));
             const uint4 a1 = ROOT ? root8(e1) : src.ld128(2 * e1), b1 = ROOT ? root8(e1 + h) : src.ld128(2 * (e1 + h));
             dst.st128(2 * e, f8(a0, b0));
@@ -525,7 +537,7 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
             const uint4 a0 = ROOT ? root8(e) : src.ld128(2 * e), b0 = ROOT ? root8(e + h) : src.ld128(2 * (e + h));
             dst.st128(2 * e, f8(a0, b0));
         }
-        __syncwarp();
+        bar();
     }
     __device__ __forceinline__ void op_f(int l) {
         if ((uint32_t)l == p.log2n) return a_sm(l - 1) ? f_t<true, false, true>(l) : f_t<true, false, false>(l);
@@ -540,9 +552,9 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
         const MemRef<DSM> dst = aref<DSM>(l - 1);
         const MemRef<BSM> bs = bref<BSM>(o);
         const uint2 z = make_uint2(0u, 0u);
-        uint32_t e = 8u * gl;
-        for (; e + 8u * G < h; e += 16u * G) {
-            const uint32_t e1 = e + 8u * G;
+        uint32_t e = 8u * gx;
+        for (; e + 8u * GX < h; e += 16u * GX) {
+            const uint32_t e1 = e + 8u * GX;
             const uint4 a0 = ROOT ? root8(e) : src.ld128(2 * e), b0 = ROOT ? root8(e + h) : src.ld128(2 * (e + h));
             const uint4 a1 = ROOT ? root8(e1) : src.ld128(2 * e1), b1 = ROOT ? root8(e1 + h) : src.ld128(2 * (e1 + h));
             const uint2 m0 = ZERO ? z : bs.ld64(e), m1 = ZERO ? z : bs.ld64(e1);
@@ -553,7 +565,7 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
             const uint4 a0 = ROOT ? root8(e) : src.ld128(2 * e), b0 = ROOT ? root8(e + h) : src.ld128(2 * (e + h));
             dst.st128(2 * e, g8<ZERO>(a0, b0, ZERO ? z : bs.ld64(e)));
         }
-        __syncwarp();
+        bar();
     }
     template <bool ZERO>
     __device__ __forceinline__ void op_g(int l, uint32_t o) {
@@ -574,7 +586,7 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
         const uint32_t h = 1u << (l - 1);
         const MemRef<CSM> cl = bref<CSM>(o), cr = bref<CSM>(o + h);
         const MemRef<DSM> d = bref<DSM>(o);
-        for (uint32_t e = 8u * gl; e < h; e += 8u * G) {
+        for (uint32_t e = 8u * gx; e < h; e += 8u * GX) {
             uint2 x = cr.ld64(e);
             if (CSM != DSM) d.st64(h + e, x);
             if (!COPY) {
@@ -584,7 +596,7 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
             }
             d.st64(e, x);
         }
-        __syncwarp();
+        bar();
     }
     template <bool COPY>
     __device__ __forceinline__ void op_h(int l, uint32_t o) {
@@ -594,8 +606,8 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
     template <bool DSM>
     __device__ __forceinline__ void r0_t(int l, uint32_t o) {
         const MemRef<DSM> d = bref<DSM>(o);
-        for (uint32_t e = 8u * gl; e < (1u << l); e += 8u * G) d.st64(e, make_uint2(0u, 0u));
-        __syncwarp();
+        for (uint32_t e = 8u * gx; e < (1u << l); e += 8u * GX) d.st64(e, make_uint2(0u, 0u));
+        bar();
     }
     __device__ __forceinline__ void op_r0(int l, uint32_t o) { return b_sm(l) ? r0_t<true>(l, o) : r0_t<false>(l, o); }
 
@@ -605,14 +617,19 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
         const MemRef<ASM> src = aref<ASM>(l);
         const MemRef<DSM> d = bref<DSM>(o);
         uint32_t z = 0;
-        for (uint32_t e = 8u * gl; e < (1u << l); e += 8u * G) {
+        for (uint32_t e = 8u * gx; e < (1u << l); e += 8u * GX) {
             const uint4 w = ROOT ? root8(e) : src.ld128(2 * e);
             z |= ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) | ((w.z - 0x01010101u) & ~w.z) |
                  ((w.w - 0x01010101u) & ~w.w);
             d.st64(e, cells_to_hd_bytes(w));
         }
-        const bool any = __any_sync(FULL, (z & 0x80808080u) != 0u);
-        __syncwarp();
+        bool any;
+        if constexpr (W == 1) {
+            any = __any_sync(FULL, (z & 0x80808080u) != 0u);
+            __syncwarp();
+        } else {
+            any = __syncthreads_or((z & 0x80808080u) != 0u) != 0;
+        }
         return any;
     }
     __device__ __forceinline__ bool op_hd(int l, uint32_t o) {
@@ -758,15 +775,17 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
 
     // subtree rooted at (LOG2S, o): alpha[LOG2S] (always in shared memory) -> partial sums of the node
     __device__ __forceinline__ void op_subtree(uint32_t o) {
-        const uint16_t* src = reinterpret_cast<const uint16_t*>(sm_alpha_p + (2u << LOG2S));
-        uint32_t a[8], b[8];
+        if (W == 1 || sub_warp) {
+            const uint16_t* src = reinterpret_cast<const uint16_t*>(sm_alpha_p + (2u << LOG2S));
+            uint32_t a[8], b[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) a[r] = prmt((uint32_t)src[G * r + gl], 0u, 0x9180);
-        local<8, 0>(a, b);
-        uint8_t* d = sm_beta_p + (o & ((2u << p.lsb) - 1u));
+            for (int r = 0; r < 8; r++) a[r] = prmt((uint32_t)src[G * r + gl], 0u, 0x9180);
+            local<8, 0>(a, b);
+            uint8_t* d = sm_beta_p + (o & ((2u << p.lsb) - 1u));
 #pragma unroll
-        for (int r = 0; r < 8; r++) d[G * r + gl] = (uint8_t)mask_to_byte(b[r]);
-        __syncwarp();
+            for (int r = 0; r < 8; r++) d[G * r + gl] = (uint8_t)mask_to_byte(b[r]);
+        }
+        bar();
     }
 
     __device__ __forceinline__ void run() {
@@ -808,7 +827,7 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
     template <bool SM>
     __device__ __forceinline__ void write_output_t(uint32_t* outA, uint32_t* outB) {
         const MemRef<SM> b = bref<SM>(0u);
-        for (uint32_t w = gl; w < p.wpf; w += G) {
+        for (uint32_t w = gx; w < p.wpf; w += GX) {
             uint32_t ba = 0u, bb = 0u;
 #pragma unroll
             for (int q = 0; q < 2; q++) {
@@ -823,7 +842,7 @@ struct FastDecoder : LeafCtx<G, LOG2PAR, EXT> {
             if (outA) outA[w] = ba;
             if (outB) outB[w] = bb;
         }
-        __syncwarp();
+        bar();
     }
     __device__ __forceinline__ void write_output(uint32_t* outA, uint32_t* outB) {
         return b_sm((int)p.log2n) ? write_output_t<true>(outA, outB) : write_output_t<false>(outA, outB);
@@ -842,6 +861,8 @@ __global__ void __launch_bounds__(256) sc_decode_fast_kernel(const FastParams p)
 
     FastDecoder<G, LOG2PAR, EXT> d(p);
     d.gl = lane % G;
+    d.gx = d.gl;
+    d.sub_warp = true;
     d.satp = p.satv * 0x00010001u;
     d.satn = ((0u - p.satv) & 0xFFFFu) * 0x00010001u;
     d.sm_alpha_p = smem_fast + slot * p.sm_stride;
@@ -864,6 +885,34 @@ __global__ void __launch_bounds__(256) sc_decode_fast_kernel(const FastParams p)
         d.llrB = p.llr + fb * p.n;
         d.run();
         d.write_output(valid ? p.xhat + fa * p.wpf : nullptr, (valid && has_b) ? p.xhat + fb * p.wpf : nullptr);
+    }
+}
+
+// One CTA of W warps per frame pair (FastDecoder<32, ..., W>): shared memory and workspace hold one pair.
+template <int LOG2PAR, bool EXT, int W>
+__global__ void __launch_bounds__(32 * W) sc_decode_fast_coop_kernel(const FastParams p) {
+    extern __shared__ __align__(16) uint8_t smem_fast[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FastDecoder<32, LOG2PAR, EXT, W> d(p);
+    d.gl = lane;
+    d.gx = (int)threadIdx.x;
+    d.sub_warp = warp == 0;
+    d.satp = p.satv * 0x00010001u;
+    d.satn = ((0u - p.satv) & 0xFFFFu) * 0x00010001u;
+    d.sm_alpha_p = smem_fast;
+    d.sm_beta_p = d.sm_alpha_p + 2u * p.sm_alpha_cells;
+    d.sm_alpha_a = smem_u32(d.sm_alpha_p);
+    d.sm_beta_a = smem_u32(d.sm_beta_p);
+    d.gl_alpha = p.ws + (unsigned long long)blockIdx.x * p.ws_stride;
+    d.gl_beta = d.gl_alpha + 4ull * p.n;
+    for (unsigned long long fp = blockIdx.x; fp < p.num_fp; fp += gridDim.x) {  // CTA-uniform
+        const unsigned long long fa = 2 * fp;
+        const bool has_b = fa + 1 < p.nframes;
+        const unsigned long long fb = has_b ? fa + 1 : fa;
+        d.llrA = p.llr + fa * p.n;
+        d.llrB = p.llr + fb * p.n;
+        d.run();
+        d.write_output(p.xhat + fa * p.wpf, has_b ? p.xhat + fb * p.wpf : nullptr);
     }
 }
 

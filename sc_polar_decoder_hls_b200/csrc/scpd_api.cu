@@ -99,6 +99,7 @@ using namespace scpd;
 
 struct FastPlan {
     int group = 0, warps = 4, log2s = 0, ctas_per_sm = 1;
+    int coop = 0;  // > 0: CTA-cooperative variant, `coop` warps walk one frame pair (group = 32, one pair per CTA)
     std::vector<uint32_t> sched_host;
     ScheduleStats stats;
     uint32_t* d_sched = nullptr;
@@ -202,6 +203,14 @@ static fast_kernel_t fast_kernel_ptr(int group, int log2par, int ext) {
     return nullptr;
 }
 
+static fast_kernel_t fast_coop_kernel_ptr(int log2par, int ext, int w) {
+    if (log2par == 4 && ext == 1) {
+        if (w == 4) return sc_decode_fast_coop_kernel<4, true, 4>;
+        if (w == 8) return sc_decode_fast_coop_kernel<4, true, 8>;
+    }
+    return nullptr;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
@@ -297,20 +306,23 @@ static int plan_bs(scpd_decoder* d, const uint8_t* flags) {
 
 // Size the shared-memory / workspace layout of the fast kernel with g lanes per frame pair.  fp->group stays 0
 // when the kernel does not apply to this configuration.
-static int plan_fast_g(scpd_decoder* d, const uint8_t* flags, int g, FastPlan* fp) {
+static int plan_fast_g(scpd_decoder* d, const uint8_t* flags, int g, FastPlan* fp, int coop = 0) {
     fp->group = 0;
-    fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
+    fp->coop = coop;
+    if (coop) g = 32;
+    fast_kernel_t k = coop ? fast_coop_kernel_ptr(d->log2par, (int)d->cfg.extended, coop)
+                           : fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
     if (!k) return SCPD_OK;
     const int log2s = ilog2(8 * g);
     if (d->log2par > log2s || d->log2n < log2s + 1 || d->cfg.n < 32) return SCPD_OK;  // leaf must sit inside the register subtree
     fp->log2s = log2s;
     fp->sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, (int)d->cfg.pruning, flags,
                                     &fp->stats, log2s);
-    fp->warps = std::max(1, std::min(8, env_int("SCPD_WARPS", 8)));
+    fp->warps = coop ? coop : std::max(1, std::min(8, env_int("SCPD_WARPS", 8)));
     const int gpw = 32 / g;
-    const int fp_per_cta = fp->warps * gpw;
+    const int fp_per_cta = coop ? 1 : fp->warps * gpw;
     const size_t budget = (size_t)env_int("SCPD_SMEM_KB", 100) * 1024;
-    const size_t per_fp = budget / fp_per_cta;
+    const size_t per_fp = coop ? budget / 8 : budget / fp_per_cta;  // cooperative: one pair per CTA, many CTAs per SM
     const uint32_t n = d->cfg.n;
     // Shared memory per frame pair: alpha levels log2s..lsa as cells (level l at cell (1 << l): 2 << lsa
     // cells), then the partial-sum block (one byte per element, 2^(lsb+1) bytes, at most n).
@@ -347,8 +359,8 @@ static int plan_fast_g(scpd_decoder* d, const uint8_t* flags, int g, FastPlan* f
     fp->ctas_per_sm = occ;
     fp->group = g;
     if (env_int("SCPD_VERBOSE", 0))
-        fprintf(stderr, "[scpd] fast kernel G=%d warps/CTA=%d: alpha levels <=%d and partial sums <=%d in smem, "
-                "%zu B/pair, %zu B/CTA, %d CTAs/SM, workspace %llu B/pair\n", g, fp->warps, lsa, lsb, stride,
+        fprintf(stderr, "[scpd] fast kernel G=%d warps/CTA=%d%s: alpha levels <=%d and partial sums <=%d in smem, "
+                "%zu B/pair, %zu B/CTA, %d CTAs/SM, workspace %llu B/pair\n", g, fp->warps, coop ? " (one pair per CTA)" : "", lsa, lsb, stride,
                 fp->smem_bytes, occ, fp->ws_stride);
     return SCPD_OK;
 }
@@ -360,13 +372,21 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
     const char* ksel = std::getenv("SCPD_KERNEL");
     if (ksel && std::strcmp(ksel, "generic") == 0) return SCPD_OK;
     if (d->cfg.format != SCPD_FMT_CA2 || d->cfg.llr_bits > 8 || d->log2par < 1) return SCPD_OK;
-    const bool pinned_group = std::getenv("SCPD_GROUP") != nullptr;
-    int rc = plan_fast_g(d, flags, env_int("SCPD_GROUP", 8), &d->fast);
+    const bool pinned_group = std::getenv("SCPD_GROUP") != nullptr || std::getenv("SCPD_COOP") != nullptr;
+    int rc = plan_fast_g(d, flags, env_int("SCPD_GROUP", 8), &d->fast, env_int("SCPD_COOP", 0));
     if (rc == SCPD_OK && !d->fast.group) rc = plan_fast_g(d, flags, 8, &d->fast);
     if (rc != SCPD_OK || !d->fast.group || pinned_group) return rc;
     for (int g = 2 * d->fast.group; g <= 32; g *= 2) {
         FastPlan w;
         rc = plan_fast_g(d, flags, g, &w);
+        if (rc != SCPD_OK) return rc;
+        if (w.group) d->fast_wide.push_back(std::move(w));
+    }
+    // beyond a warp per pair: the CTA-cooperative variant.  Measured gain from N = 2^15 up (N = 2^19, 1024 frames:
+    // 17 -> 26 Gb/s); at N = 4096 the register subtrees dominate and it loses 10 %
+    for (int cw = 4; cw <= 8 && d->log2n >= 14; cw *= 2) {
+        FastPlan w;
+        rc = plan_fast_g(d, flags, 32, &w, cw);
         if (rc != SCPD_OK) return rc;
         if (w.group) d->fast_wide.push_back(std::move(w));
     }
@@ -379,7 +399,7 @@ static const FastPlan& pick_fast(const scpd_decoder* d, unsigned long long num_f
     const FastPlan* best = &d->fast;
     const unsigned long long lanes_wanted = (unsigned long long)d->num_sms * (unsigned)env_int("SCPD_FAST_WIDE_LANES", 256);
     for (const FastPlan& w : d->fast_wide)
-        if (num_fp * (unsigned)best->group < lanes_wanted) best = &w;
+        if (num_fp * (unsigned)(best->coop ? 32 * best->coop : best->group) < lanes_wanted) best = &w;
     return *best;
 }
 
@@ -588,7 +608,7 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     const unsigned long long num_fp = (nframes + 1) / 2;
     const FastPlan& fp = pick_fast(d, num_fp);
     const int g = fp.group, gpw = 32 / g;
-    const unsigned long long fp_per_cta = (unsigned long long)fp.warps * gpw;
+    const unsigned long long fp_per_cta = fp.coop ? 1ull : (unsigned long long)fp.warps * gpw;
     unsigned long long grid = (num_fp + fp_per_cta - 1) / fp_per_cta;
     const unsigned long long max_grid = (unsigned long long)d->num_sms * fp.ctas_per_sm;
     if (grid > max_grid) grid = max_grid;
@@ -617,7 +637,8 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     p.sm_stride = fp.sm_stride;
     p.ws = d->d_fast_ws;
     p.ws_stride = fp.ws_stride;
-    fast_kernel_t k = fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
+    fast_kernel_t k = fp.coop ? fast_coop_kernel_ptr(d->log2par, (int)d->cfg.extended, fp.coop)
+                              : fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(fp.warps * 32)), fp.smem_bytes, st>>>(p);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));

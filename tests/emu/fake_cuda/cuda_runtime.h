@@ -31,6 +31,7 @@ extern thread_local LaneCtx* cur;
 uint32_t collective_exchange(uint32_t v, int src_lane);  // returns value contributed by src_lane
 uint32_t collective_ballot(bool pred);
 void collective_sync();
+int cta_barrier_or(int pred);  // __syncthreads_or over the emulated CTA
 }  // namespace cuda_emu
 #define threadIdx (cuda_emu::cur->tid)
 #define blockIdx (cuda_emu::cur->bid)
@@ -42,8 +43,10 @@ static inline T __ldg(const T* p) { return *p; }
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cuda_emu::collective_sync(); }
-// the emulator runs the warps of a CTA one after the other; kernels must not rely on this under emulation
-static inline void __syncthreads() { cuda_emu::collective_sync(); }
+// CTA barrier over the fibers of run_cta (kernels whose warps are emulated one after the other through run_warp
+// see a CTA of one warp and must not rely on cross-warp state under emulation)
+static inline void __syncthreads() { (void)cuda_emu::cta_barrier_or(0); }
+static inline int __syncthreads_or(int pred) { return cuda_emu::cta_barrier_or(pred); }
 static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src, int width = 32) {
     const int lane = cuda_emu::cur->lane;
     return cuda_emu::collective_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));

@@ -24,90 +24,121 @@ namespace cuda_emu {
 thread_local LaneCtx* cur = nullptr;
 namespace {
 constexpr int W = 32;
-struct Warp {
+constexpr int MAXW = 8;  // warps per emulated CTA
+// One CTA: nw warps of 32 fibers.  Warp collectives are resolved per warp, __syncthreads over all fibers.
+struct Cta {
+    int nw = 1;
     ucontext_t main_ctx;
-    ucontext_t ctx[W];
-    std::vector<char> stacks[W];
-    LaneCtx lanes[W];
-    bool done[W];
+    ucontext_t ctx[MAXW * W];
+    std::vector<char> stacks[MAXW * W];
+    LaneCtx lanes[MAXW * W];
+    bool done[MAXW * W];
     int running = 0;
-    uint32_t exch[2][W];
-    unsigned long long arrivals[2] = {0, 0};
-    unsigned long long phase[W];
+    uint32_t exch[MAXW][2][W];
+    unsigned long long arrivals[MAXW][2];
+    unsigned long long phase[MAXW * W];
+    uint32_t cta_exch[2][MAXW * W];
+    unsigned long long cta_arrivals[2] = {0, 0};
+    unsigned long long cta_phase[MAXW * W];
     void (*body)(void*) = nullptr;
     void* arg = nullptr;
 };
-Warp* g_warp = nullptr;
+Cta* g_cta = nullptr;
 void yield_lane() {
-    Warp* w = g_warp;
-    const int me = w->running;
-    swapcontext(&w->ctx[me], &w->main_ctx);
+    Cta* c = g_cta;
+    const int me = c->running;
+    swapcontext(&c->ctx[me], &c->main_ctx);
 }
-int arrive(uint32_t v) {  // returns buffer index; blocks until all lanes have arrived
-    Warp* w = g_warp;
-    const int me = w->running;
-    const unsigned long long ph = w->phase[me]++;
+int arrive(uint32_t v) {  // warp collective: returns buffer index; blocks until the 32 lanes of the warp have arrived
+    Cta* c = g_cta;
+    const int me = c->running, wi = me / W;
+    const unsigned long long ph = c->phase[me]++;
     const int buf = (int)(ph & 1);
-    w->exch[buf][me] = v;
-    w->arrivals[buf]++;
-    while (w->arrivals[buf] < (unsigned long long)W * (ph / 2 + 1)) yield_lane();
+    c->exch[wi][buf][me % W] = v;
+    c->arrivals[wi][buf]++;
+    while (c->arrivals[wi][buf] < (unsigned long long)W * (ph / 2 + 1)) yield_lane();
+    return buf;
+}
+int cta_arrive(uint32_t v) {  // CTA barrier over all fibers
+    Cta* c = g_cta;
+    const int me = c->running;
+    const unsigned long long ph = c->cta_phase[me]++;
+    const int buf = (int)(ph & 1);
+    c->cta_exch[buf][me] = v;
+    c->cta_arrivals[buf]++;
+    while (c->cta_arrivals[buf] < (unsigned long long)W * c->nw * (ph / 2 + 1)) yield_lane();
     return buf;
 }
 void trampoline() {
-    Warp* w = g_warp;
-    const int me = w->running;
-    cur = &w->lanes[me];
-    w->body(w->arg);
-    w->done[me] = true;
-    swapcontext(&w->ctx[me], &w->main_ctx);
+    Cta* c = g_cta;
+    const int me = c->running;
+    cur = &c->lanes[me];
+    c->body(c->arg);
+    c->done[me] = true;
+    swapcontext(&c->ctx[me], &c->main_ctx);
 }
 }  // namespace
 uint32_t collective_exchange(uint32_t v, int src_lane) {
+    const int wi = g_cta->running / W;
     const int buf = arrive(v);
-    return g_warp->exch[buf][src_lane & 31];
+    return g_cta->exch[wi][buf][src_lane & 31];
 }
 uint32_t collective_ballot(bool pred) {
+    const int wi = g_cta->running / W;
     const int buf = arrive(pred ? 1u : 0u);
     uint32_t r = 0;
-    for (int i = 0; i < W; i++) r |= (g_warp->exch[buf][i] & 1u) << i;
+    for (int i = 0; i < W; i++) r |= (g_cta->exch[wi][buf][i] & 1u) << i;
     return r;
 }
 void collective_sync() { (void)arrive(0); }
+int cta_barrier_or(int pred) {
+    const int buf = cta_arrive(pred ? 1u : 0u);
+    uint32_t r = 0;
+    for (int i = 0; i < W * g_cta->nw; i++) r |= g_cta->cta_exch[buf][i];
+    return r != 0;
+}
 
-// run one warp (32 lanes) of `body` to completion
-void run_warp(void (*body)(void*), void* arg, dim3 block, dim3 grid, dim3 bdim, int warp_index) {
-    Warp* w = new Warp();
-    g_warp = w;
-    w->body = body;
-    w->arg = arg;
-    for (int i = 0; i < W; i++) {
-        w->stacks[i].resize(1 << 18);
-        w->done[i] = false;
-        w->phase[i] = 0;
-        w->lanes[i].tid.x = warp_index * 32 + i;
-        w->lanes[i].bid = block;
-        w->lanes[i].gdim = grid;
-        w->lanes[i].bdim = bdim;
-        w->lanes[i].lane = i;
-        getcontext(&w->ctx[i]);
-        w->ctx[i].uc_stack.ss_sp = w->stacks[i].data();
-        w->ctx[i].uc_stack.ss_size = w->stacks[i].size();
-        w->ctx[i].uc_link = &w->main_ctx;
-        makecontext(&w->ctx[i], (void (*)())trampoline, 0);
+// run warps [first_warp, first_warp + nw) of a CTA of `body` concurrently to completion
+void run_cta(void (*body)(void*), void* arg, dim3 block, dim3 grid, dim3 bdim, int first_warp, int nw) {
+    Cta* c = new Cta();
+    g_cta = c;
+    c->nw = nw;
+    c->body = body;
+    c->arg = arg;
+    std::memset(c->arrivals, 0, sizeof c->arrivals);
+    for (int i = 0; i < W * nw; i++) {
+        c->stacks[i].resize(1 << 18);
+        c->done[i] = false;
+        c->phase[i] = 0;
+        c->cta_phase[i] = 0;
+        c->lanes[i].tid.x = first_warp * 32 + i;
+        c->lanes[i].bid = block;
+        c->lanes[i].gdim = grid;
+        c->lanes[i].bdim = bdim;
+        c->lanes[i].lane = i % W;
+        getcontext(&c->ctx[i]);
+        c->ctx[i].uc_stack.ss_sp = c->stacks[i].data();
+        c->ctx[i].uc_stack.ss_size = c->stacks[i].size();
+        c->ctx[i].uc_link = &c->main_ctx;
+        makecontext(&c->ctx[i], (void (*)())trampoline, 0);
     }
     for (;;) {
         bool all = true;
-        for (int i = 0; i < W; i++) {
-            if (w->done[i]) continue;
+        for (int i = 0; i < W * nw; i++) {
+            if (c->done[i]) continue;
             all = false;
-            w->running = i;
-            cur = &w->lanes[i];
-            swapcontext(&w->main_ctx, &w->ctx[i]);
+            c->running = i;
+            cur = &c->lanes[i];
+            swapcontext(&c->main_ctx, &c->ctx[i]);
         }
         if (all) break;
     }
-    delete w;
-    g_warp = nullptr;
+    delete c;
+    g_cta = nullptr;
+}
+// one warp on its own (kernels whose warps do not synchronise with each other run warp after warp)
+void run_warp(void (*body)(void*), void* arg, dim3 block, dim3 grid, dim3 bdim, int warp_index) {
+    run_cta(body, arg, block, grid, bdim, warp_index, 1);
 }
 }  // namespace cuda_emu
 
@@ -183,6 +214,61 @@ int emu_fast_decode(int g, int log2n, int log2par, int llr_bits, int extended, i
         dim3 bi;
         bi.x = (unsigned)b;
         for (int w = 0; w < warps; w++) cuda_emu::run_warp(body, &L, bi, gd, bd, w);
+    }
+    return 0;
+}
+
+// Emulates the CTA-cooperative variant of the fast kernel (W warps walk one frame pair together; the fibers of
+// all W warps run concurrently with a real CTA barrier).  Returns 0, -1 if W is not compiled in.
+int emu_fast_coop_decode(int w, int log2n, int log2par, int llr_bits, int extended, int pruning, const uint8_t* flags,
+                         const int8_t* llr, size_t nframes, uint32_t* xhat, int lsa, int lsb, int grid) {
+    struct CL {
+        FastParams p;
+    } L;
+    void (*body)(void*) = nullptr;
+    if (log2par == 4 && extended) {
+        if (w == 2) body = [](void* a) { sc_decode_fast_coop_kernel<4, true, 2>(static_cast<CL*>(a)->p); };
+        if (w == 4) body = [](void* a) { sc_decode_fast_coop_kernel<4, true, 4>(static_cast<CL*>(a)->p); };
+        if (w == 8) body = [](void* a) { sc_decode_fast_coop_kernel<4, true, 8>(static_cast<CL*>(a)->p); };
+    }
+    if (!body) return -1;
+    const int ls = 8;  // register subtree of 8 * 32 elements
+    if (log2n < ls + 1) return -2;
+    ScheduleStats st;
+    std::vector<uint32_t> sched = build_schedule(log2n, log2par, extended, pruning, flags, &st, ls);
+    const uint32_t n = 1u << log2n;
+    FastParams& p = L.p;
+    p.sched = sched.data();
+    p.llr = llr;
+    p.xhat = xhat;
+    p.nframes = nframes;
+    p.num_fp = (nframes + 1) / 2;
+    p.n = n;
+    p.log2n = (uint32_t)log2n;
+    p.wpf = n / 32;
+    p.satv = (1u << (llr_bits - 1)) - 1u;
+    if (lsa < 0) lsa = log2n - 1;
+    if (lsb < 0) lsb = log2n;
+    if (lsa < ls) lsa = ls;
+    if (lsb < ls) lsb = ls;
+    p.lsa = (uint32_t)lsa;
+    p.lsb = (uint32_t)lsb;
+    p.sm_alpha_cells = 2u << lsa;
+    const size_t beta_bytes = std::min<size_t>((size_t)2u << lsb, n);
+    const size_t stride = ((size_t)p.sm_alpha_cells * 2 + beta_bytes + 127) & ~(size_t)127;
+    p.sm_stride = (uint32_t)stride;
+    if (stride > sizeof(smem_fast)) return -3;
+    p.ws_stride = ((unsigned long long)n * 5ull + 255ull) & ~255ull;
+    std::vector<uint8_t> ws((size_t)grid * p.ws_stride + 256, 0xCD);
+    p.ws = reinterpret_cast<uint8_t*>(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
+    dim3 gd, bd;
+    gd.x = (unsigned)grid;
+    bd.x = (unsigned)w * 32;
+    for (int b = 0; b < grid; b++) {
+        std::memset(smem_fast, 0xEE, sizeof(smem_fast));
+        dim3 bi;
+        bi.x = (unsigned)b;
+        cuda_emu::run_cta(body, &L, bi, gd, bd, 0, w);
     }
     return 0;
 }

@@ -64,17 +64,20 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
     dec.close()
 
 
-@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "bs8", "bs16", "bs32", "bs32ws"])
+@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "coop4", "coop8", "bs8", "bs16", "bs32", "bs32ws"])
 def kernel_mode(request, monkeypatch):
     """Selects the decode kernel through the library's environment switches (read in scpd_create):
     the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
     workspace early, one warp per CTA), the int16x2 kernel with 2 / 8 / 16 lanes per frame pair, the
     generic kernel, the raw-pattern kernel, and the library's own choice."""
     mode = request.param
-    for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS"):
+    for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_COOP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS"):
         monkeypatch.delenv(v, raising=False)
     if mode in ("generic", "raw"):
         monkeypatch.setenv("SCPD_KERNEL", mode)
+    elif mode.startswith("coop"):
+        monkeypatch.setenv("SCPD_KERNEL", "fast")
+        monkeypatch.setenv("SCPD_COOP", mode[4:])
     elif mode.startswith("fast"):
         monkeypatch.setenv("SCPD_KERNEL", "fast")
         monkeypatch.setenv("SCPD_GROUP", mode[4:])
@@ -90,7 +93,7 @@ def kernel_mode(request, monkeypatch):
 @pytest.mark.parametrize("key,nfr", [("c1", 600), ("c2", 150), ("c3", 8)])
 @pytest.mark.parametrize("prune", [0, 1, 2])
 def test_every_kernel_variant(scpd, kernel_mode, key, nfr, prune):
-    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8"):
+    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8", "coop4"):
         pytest.skip("the large tree is covered by one variant per kernel family")
     name, n, k, snr = CONFIG_SETS[key]
     llr = _llrs(21, n, nfr, k, snr).copy()

@@ -234,3 +234,32 @@ def test_stage_profile_matches_reference_fsm_trip_counts():
     rnd = np.random.default_rng(0)
     bad = scpd.Config(48, 1, 16, 8, 0, 1, 0, 0)
     assert scpd.lib.scpd_stage_profile(ctypes.byref(bad), ol.P(flags), ctypes.byref(scpd.StageMatrix())) == scpd.E_CONFIG
+
+
+def _cemu(w, flags, n, prune, llr, lsa=-1, lsb=-1, grid=1):
+    out = np.zeros((len(llr), n // 32), np.uint32)
+    rc = _emu_lib('libwarp_emu.so').emu_fast_coop_decode(w, int(np.log2(n)), 4, 8, 1, prune, ol.P(flags), ol.P(llr),
+                                                         ctypes.c_size_t(len(llr)), ol.P(out), lsa, lsb, grid)
+    assert rc == 0, rc
+    return out
+
+
+@pytest.mark.parametrize("w", [2, 4, 8])
+def test_cooperative_fast_kernel_under_cta_emulator(w):
+    """The CTA-cooperative variant of decode_fast.cuh (W warps walk one frame pair; small batches of large trees):
+    all W warps emulated concurrently with a real CTA barrier, every pruning mode, zero-LLR frames (rate-1 fallback
+    decided CTA-wide), levels split between shared memory and workspace, odd batch, several pairs per CTA."""
+    rng = np.random.default_rng(w)
+    sets = [("FB_N1024_K512", 1024, 512, (0, 1, 2))]
+    if w == 4:
+        sets.append(("frozen_n_4096_k_3072", 4096, 3072, (2,)))
+    for name, n, k, prunes in sets:
+        flags = scpd.packed_flags(name, n)
+        llr = ol.test_llrs(rng, n, 5 if n == 1024 else 3, k)
+        llr[0] = 0
+        llr[1][::5] = 0
+        want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+        for prune in prunes:
+            assert (_cemu(w, flags, n, prune, llr, grid=2) == want).all(), (n, prune)
+        ls = int(np.log2(n)) - 2
+        assert (_cemu(w, flags, n, 2, llr, lsa=ls, lsb=ls - 1, grid=1) == want).all(), (n, "workspace")
