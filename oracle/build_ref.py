@@ -43,6 +43,10 @@ CONFIGS = [
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 8, "sm", 1),
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 6, "sm", 0),
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 64, 7, "sm", 1),
+    # configurations only the raw-pattern kernel covers: wrapping 5-bit alphabet in SIGMAG, 17-bit leaf, SIGMAG Q 9
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 5, "sm", 1),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 256, 9, "ca2", 1),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 4, 9, "sm", 1),
     # BASELINE configs 2..5 at the headline setting
     (4096, 3072, "Generated_Frozen_Bit/frozen_n_4096_k_3072.txt", 1, 16, 8, "ca2", 1),
     (32768, 29492, "Generated_Frozen_Bit/frozen_n_32768_k_29492_snr_4_5.txt", 1, 16, 8, "ca2", 1),

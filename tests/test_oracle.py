@@ -46,6 +46,8 @@ REF_TAGS = [("n8_p2_q8_ca2_e1", "FB_N8_K4", 300), ("n8_p4_q6_sm_e1", "FB_N8_K4",
             ("n1024_p16_q5_ca2_e1", "FB_N1024_K512", 30), ("n1024_p16_q9_ca2_e1", "FB_N1024_K512", 30),
             ("n1024_p16_q6_sm_e1", "FB_N1024_K512", 30), ("n1024_p16_q8_sm_e1", "FB_N1024_K512", 30),
             ("n1024_p16_q6_sm_e0", "FB_N1024_K512", 30), ("n1024_p64_q7_sm_e1", "FB_N1024_K512", 20),
+            ("n1024_p16_q5_sm_e1", "FB_N1024_K512", 30), ("n1024_p256_q9_ca2_e1", "FB_N1024_K512", 20),
+            ("n1024_p4_q9_sm_e1", "FB_N1024_K512", 30),
             ("n4096_p16_q8_ca2_e1", "frozen_n_4096_k_3072", 8),
             ("n32768_p16_q8_ca2_e1", "frozen_n_32768_k_29492_snr_4_5", 2)]
 
@@ -65,6 +67,7 @@ def test_oracle_equals_reference_compiled_natively(tag, name, nfr):
     llr = ol.test_llrs(rng, n, nfr, int(flags.sum()))
     llr[-1] = rng.integers(-31, 32, size=n)
     llr[-1][rng.random(n) < 0.4] = 0  # exercise the zero / tie rules
+    llr[-2] = rng.integers(-128, 128, size=n)  # beyond every LLR_BITS here: truncation on the sc_fifo<LLR> write
     assert (ol.ref_decode(R, flags, llr) == ol.decode(n, par, q, fmt, ext, flags, llr)).all()
 
 
