@@ -47,6 +47,10 @@ CONFIGS = [
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 5, "sm", 1),
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 256, 9, "ca2", 1),
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 4, 9, "sm", 1),
+    # the reference's checked-in default (config.h): SIGMAG, LLR_BITS 6, PRUNING_LEVEL 2 with R1 / REP / SPC / H0 --
+    # NOT the plain-SC contract of this library; built to measure how far the reference's own pruning departs from it
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 6, "sm", 1, 2),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 8, "ca2", 1, 2),
     # BASELINE configs 2..5 at the headline setting
     (4096, 3072, "Generated_Frozen_Bit/frozen_n_4096_k_3072.txt", 1, 16, 8, "ca2", 1),
     (32768, 29492, "Generated_Frozen_Bit/frozen_n_32768_k_29492_snr_4_5.txt", 1, 16, 8, "ca2", 1),
@@ -56,8 +60,9 @@ CONFIGS = [
 
 
 def tag(cfg):
-    n, k, src, isflag, par, q, fmt, ext = cfg
-    return f"n{n}_p{par}_q{q}_{fmt}_e{ext}"
+    n, k, src, isflag, par, q, fmt, ext = cfg[:8]
+    pl = cfg[8] if len(cfg) > 8 else 0
+    return f"n{n}_p{par}_q{q}_{fmt}_e{ext}" + (f"_pl{pl}" if pl else "")
 
 
 def sh(cmd, **kw):
@@ -88,22 +93,23 @@ CONFIG_H = """
 
 #define EXTENDED		{ext}
 
-#define PRUNING_LEVEL 	0
+#define PRUNING_LEVEL 	{pl}
 
-#define ELAG_R1			0
-#define ELAG_REP		0
-#define ELAG_SPC		0
+#define ELAG_R1			{on}
+#define ELAG_REP		{on}
+#define ELAG_SPC		{on}
 #define ELAG_REP2		0
 #define ELAG_SPC2		0
 #define ELAG_RARE		0
-#define ELAG_H0			0
+#define ELAG_H0			{on}
 
 #define _MONITORING_
 """
 
 
 def build_one(ref, cfg, cxx):
-    n, k, src, isflag, par, q, fmt, ext = cfg
+    n, k, src, isflag, par, q, fmt, ext = cfg[:8]
+    pl = cfg[8] if len(cfg) > 8 else 0  # PRUNING_LEVEL; > 0 switches the checked-in ELAG_* defaults on (config.h:16-30)
     t = tag(cfg)
     so = os.path.join(OUT, f"refdec_{t}.so")
     work = os.path.join(OUT, "work", t)
@@ -118,7 +124,7 @@ def build_one(ref, cfg, cxx):
     # config.h in the reference's own macro vocabulary (the sweep scripts rewrite it the same way,
     # script/script_tests.sh:24-53)
     open(os.path.join(mod, "config.h"), "w").write(
-        CONFIG_H.format(q=q, fmt="CA2" if fmt == "ca2" else "SIGMAG", ext=ext))
+        CONFIG_H.format(q=q, fmt="CA2" if fmt == "ca2" else "SIGMAG", ext=ext, pl=pl, on=1 if pl else 0))
     for h in ("my_module.h", "wrapper_in.h", "wrapper_out.h"):
         symlink(os.path.join(ref, "src", "module", h), os.path.join(mod, h))
     symlink(os.path.join(ref, "shared"), os.path.join(work, "tree", "shared"))

@@ -148,3 +148,22 @@ def test_rate1_hard_decision_rule():
     assert (ol.decode(n, 16, 8, 0, 1, flags, z) != (z < 0)).any(axis=1).sum() > 400
     sm = ol.decode(n, 16, 8, 1, 1, flags, z)
     assert (sm == (z < 0)).all()
+
+
+@pytest.mark.parametrize("tag,q,fmt", [("n1024_p16_q6_sm_e1_pl2", 6, 1), ("n1024_p16_q8_ca2_e1_pl2", 8, 0)])
+def test_reference_full_pruning_is_not_plain_sc(tag, q, fmt):
+    """Why REP / SPC pruning is not one of this library's modes: the reference compiled with
+    its checked-in PRUNING_LEVEL 2 (R1 / REP / SPC / H0, config.h:16-30) returns the golden codewords and agrees with
+    plain SC on clean frames, but departs from it on noisy ones -- so it is a different decoder, not a shortcut."""
+    R = ol.ref_lib(tag)
+    if R is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    n, k = 1024, 512
+    flags = scpd.packed_flags("FB_N1024_K512", n)
+    cws = ol.golden_codewords()["cw1024x512"]
+    assert (ol.ref_decode(R, flags, np.where(cws == 1, -4, 4).astype(np.int8)) == cws).all()
+    clean = ol.channel(n, 100, ol.sigma(4.0, k / n))
+    assert (ol.ref_decode(R, flags, clean) == ol.decode(n, 16, q, fmt, 1, flags, clean)).all()
+    noisy = ol.channel(n, 200, ol.sigma(1.0, k / n))
+    differ = (ol.ref_decode(R, flags, noisy) != ol.decode(n, 16, q, fmt, 1, flags, noisy)).any(axis=1)
+    assert 0 < differ.sum() < len(noisy)
