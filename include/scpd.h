@@ -123,6 +123,9 @@ int scpd_kernel_timing(scpd_decoder* dec, int enable);
 int scpd_last_kernel_ms(scpd_decoder* dec, float* ms);
 /* Which kernel family and layout this handle launches (static text, valid until the next call). */
 const char* scpd_kernel_name(const scpd_decoder* dec);
+/* The kernel the last scpd_decode of this handle launched (scpd_decode picks by batch size: bit-sliced for large
+ * batches, int16x2 with 8 / 16 / 32 lanes or a whole CTA per frame pair below); "" before the first decode. */
+const char* scpd_last_kernel_name(const scpd_decoder* dec);
 /* The function x level matrix of sc_monitor (src/rtl_simu_testbench/sc_monitor/sc_monitor.h:50-441), from
  * the frozen table alone (host only, no device needed): per FSM function and node size 2^l, the node visits
  * per frame and the trip counts of the reference's pipelined loops (f_loop / g_loop / h_loop,

@@ -82,6 +82,7 @@ public:
         return ms;
     }
     std::string kernel_name() const { return scpd_kernel_name(h_); }
+    std::string last_kernel_name() const { return scpd_last_kernel_name(h_); }
     // sc_monitor's function x level matrix for this handle's table and pruning mode (host only)
     scpd_stage_matrix stage_profile(const std::vector<uint8_t>& info_flags) const {
         scpd_stage_matrix m;

@@ -65,6 +65,7 @@ def _load():
         "scpd_kernel_timing": (c.c_int, [vp, c.c_int]),
         "scpd_last_kernel_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "scpd_kernel_name": (c.c_char_p, [vp]),
+        "scpd_last_kernel_name": (c.c_char_p, [vp]),
         "scpd_stage_profile": (c.c_int, [c.POINTER(Config), u8p, c.POINTER(StageMatrix)]),
         "scpd_sigma": (c.c_float, [c.c_float, c.c_float]),
         "scpd_channel_generate": (c.c_int, [c.c_uint32, c.c_uint64, c.c_size_t, c.c_uint8, c.c_float, vp,
@@ -87,7 +88,7 @@ EXPORTS = ["scpd_frozen_load_order", "scpd_frozen_load_flags", "scpd_frozen_writ
            "scpd_frozen_write_flags", "scpd_write_polar_parameters", "scpd_create", "scpd_destroy",
            "scpd_decode", "scpd_decode_host", "scpd_extract_info", "scpd_get_config",
            "scpd_schedule_stats", "scpd_launch_count", "scpd_kernel_timing", "scpd_last_kernel_ms",
-           "scpd_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate",
+           "scpd_kernel_name", "scpd_last_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate",
            "scpd_count_errors", "scpd_run_ber", "scpd_last_error", "scpd_status_string"]
 
 
@@ -216,6 +217,11 @@ class Decoder:
     @property
     def kernel_name(self):
         return lib.scpd_kernel_name(self._h).decode()
+
+    @property
+    def last_kernel_name(self):
+        """The kernel the last decode launched (the dispatch depends on the batch size)."""
+        return lib.scpd_last_kernel_name(self._h).decode()
 
     def kernel_timing(self, enable=True):
         check(lib.scpd_kernel_timing(self._h, 1 if enable else 0))

@@ -173,6 +173,7 @@ struct scpd_decoder {
     size_t stage_frames = 0;
     unsigned long long* d_counters = nullptr;
     uint64_t launches = 0;
+    char last_kernel[96] = "";  // what the last scpd_decode launched (scpd_last_kernel_name)
 };
 
 static const void* generic_kernel_ptr(int group) {
@@ -641,6 +642,10 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
                               : fast_kernel_ptr(g, d->log2par, (int)d->cfg.extended);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(fp.warps * 32)), fp.smem_bytes, st>>>(p);
+    if (fp.coop)
+        snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_fast_coop_kernel (int16x2, %d warps per frame pair)", fp.coop);
+    else
+        snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_fast_kernel (int16x2, %d lanes per frame pair)", g);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -707,6 +712,7 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->bs_group);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(d->bs_warps * 32)), d->bs_smem_bytes, st>>>(p);
+    snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_bs_kernel (bit-sliced, %d lanes per 32-frame group)", d->bs_group);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -748,6 +754,7 @@ static int decode_raw(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint
         sc_decode_raw_kernel<8><<<g, b, d->raw_smem_bytes, st>>>(p);
     else
         sc_decode_raw_kernel<32><<<g, b, d->raw_smem_bytes, st>>>(p);
+    snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_raw_kernel (raw W-bit patterns, %d lanes per frame)", d->raw_group);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -812,6 +819,7 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
         case 16: sc_decode_generic_kernel<16><<<g, b, d->smem_bytes, st>>>(p); break;
         default: sc_decode_generic_kernel<32><<<g, b, d->smem_bytes, st>>>(p); break;
     }
+    snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_generic_kernel (int16x2, %d lanes per frame pair)", d->group);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -928,6 +936,8 @@ extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
         snprintf(buf, sizeof buf, "sc_decode_generic_kernel (int16x2, %d lanes per frame pair)", d->group);
     return buf;
 }
+
+extern "C" const char* scpd_last_kernel_name(const scpd_decoder* d) { return d ? d->last_kernel : ""; }
 
 extern "C" int scpd_extract_info(scpd_decoder* d, const uint32_t* d_xhat, size_t nframes, uint32_t* d_uhat,
                                  void* stream) {
