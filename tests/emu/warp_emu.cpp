@@ -273,6 +273,14 @@ int emu_fast_coop_decode(int w, int log2n, int log2par, int llr_bits, int extend
     return 0;
 }
 
+// CTA mode of emu_bs_decode: all warps of a CTA run concurrently with a real CTA barrier, the schedule is copied into
+// shared memory by the CTA (BsParams::sched_words) and a barrier op is compiled in front of every sync_every-th op.
+static int g_bs_cta = 0, g_bs_sync = 0;
+void emu_bs_cta_mode(int on, int sync_every) {
+    g_bs_cta = on;
+    g_bs_sync = sync_every;
+}
+
 // Emulates the bit-sliced kernel (decode_bs.cuh).  fmt 0 = CA2, 1 = SIGMAG; g = lanes per frame group.
 // lsa/lsb < 0: planned from smem_per_group.  Returns 0, -1 if the variant is not compiled into the
 // emulator, -3 if it does not fit.
@@ -295,15 +303,15 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
     ScheduleStats st;
     std::vector<uint32_t> ops = build_schedule(log2n, log2par, extended, pruning, flags, &st, BS_LSUB, fmt == 0 ? 1 : 2);
     std::vector<uint32_t> sched;
-    if (!bs_compile_schedule(ops, &sched, 0, fuse)) return -4;
+    if (!bs_compile_schedule(ops, &sched, g_bs_cta ? g_bs_sync : 0, fuse)) return -4;
     BsPlan plan;
     if (!bs_make_plan(log2n, llr_bits, log2par, extended, (size_t)smem_per_group, &plan, lsa, lsb, g)) return -3;
     const int gpw = 32 / g;
-    if ((size_t)plan.sm_stride * warps * gpw > sizeof(smem_fast)) return -3;
+    if ((size_t)plan.sm_stride * warps * gpw + (g_bs_cta ? sched.size() * 4 : 0) > sizeof(smem_fast)) return -3;
     BsParams& p = L.p;
     p.sched = sched.data();
     p.prefetch = 0;
-    p.sched_words = 0;  // the emulator runs the warps of a CTA one after the other: no __syncthreads
+    p.sched_words = g_bs_cta ? (uint32_t)sched.size() : 0u;  // warp-after-warp emulation cannot share a CTA's schedule copy
     p.xhat = xhat;
     p.nframes = nframes;
     p.ngroups = (nframes + 31) / 32;
@@ -355,7 +363,10 @@ int emu_bs_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int exte
         std::memset(smem_fast, 0xEE, sizeof(smem_fast));
         dim3 bi;
         bi.x = (unsigned)b;
-        for (int w = 0; w < warps; w++) cuda_emu::run_warp(body, &L, bi, gd, bd, w);
+        if (g_bs_cta)
+            cuda_emu::run_cta(body, &L, bi, gd, bd, 0, warps);
+        else
+            for (int w = 0; w < warps; w++) cuda_emu::run_warp(body, &L, bi, gd, bd, w);
     }
     return 0;
 }

@@ -151,3 +151,23 @@ def test_bs_element_functions_exhaustive(fmt, q):
                 assert got == L.sco_value(0, wout, want), (op, a, b, u)
             else:
                 assert (int(so[i]) << (wout - 1)) | int(mo[i]) == want, (op, a, b, u)
+
+
+@pytest.mark.parametrize("sync_every", [0, 3])
+def test_bs_kernel_whole_cta_with_schedule_in_shared_memory(sync_every):
+    """The CTA-level paths of the headline kernel: all 4 warps of a CTA emulated concurrently with a real barrier,
+    the schedule copied into shared memory by the CTA (the default below 8 KB of schedule), optional barrier ops
+    (SCPD_BS_SYNC), several rounds per CTA and a ragged last round (warps without frames still reach every barrier)."""
+    n, k = 1024, 512
+    flags = scpd.packed_flags("FB_N1024_K512", n)
+    rng = np.random.default_rng(5 + sync_every)
+    llr = ol.test_llrs(rng, n, 32 * 9 + 5, k)  # 10 frame groups over 2 CTAs of 4 warps: 2 rounds, the second ragged
+    llr[-1][::3] = 0
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+    _emu().emu_bs_cta_mode(1, sync_every)
+    try:
+        for g, prune in ((32, 2), (16, 0)):
+            got = bs_emu(0, g, flags, n, 16, 8, 1, prune, llr, smem=7168, warps=4, grid=2 if g == 32 else 1, fuse=0)
+            assert (got == want).all(), (g, prune)
+    finally:
+        _emu().emu_bs_cta_mode(0, 0)
