@@ -1,0 +1,792 @@
+// decode_ss.cuh -- the slot-sliced SC decode kernel: every LANE decodes one frame, bit-sliced over 32
+// consecutive code positions ("a chunk"); the bottom of the tree runs as fp16x2 arithmetic on the FMA pipe.
+//
+// Why (profiles/ncu_r1_bs_c2_summary.txt): the frame-sliced kernel (decode_bs.cuh: one register = one bit of
+// one LLR for 32 FRAMES, the lanes of a warp spread over the LLRs of a node) keeps only n/2 lanes busy on a
+// node of n <= 32 LLRs and walks those nodes through shared memory, which cost 5.4x the instructions of the
+// plane arithmetic.  Turning the slicing by 90 degrees removes the problem:
+//   * a 32-bit register holds one bit plane of 32 CONSECUTIVE LLRs of ONE frame; lane = frame, a warp = 32 frames
+//     that share nothing but the schedule.  f / g of a node of n >= 64 LLRs are the same LOP3 sequences as before
+//     (bs_arith.cuh: f 2P+1, saturating g 5P+2 for P magnitude planes) on n/64 independent chunk pairs per lane:
+//     every lane is busy at every level, there is no cross-lane traffic, no __syncwarp, and the partial sums
+//     (one bit per code position) are already the packed output words -- no transposition on the way out.
+//   * a node of 32 LLRs is one chunk.  Its sign-magnitude planes are transposed IN the lane (three delta-swap
+//     stages on 8 registers) into sign-magnitude bytes, and a sign-magnitude byte spread to 16 bits IS an fp16
+//     denormal of the same value: 16 registers of fp16x2 hold the node.  Below that, f(a,b) = (|a+b| - |a-b|)/2
+//     is three HADD2 (the factor 2 is carried as a static scale: f, g and the hard decisions are homogeneous),
+//     g(a,b,u) = b + (1-2u) a is one HFMA2 with the partial sum kept as +-1.0, h is one HMUL2, and the hard
+//     decision is the sign bit.  All values are integers below 2^11 times a power of two, so fp16 is exact;
+//     x - x = +0 in round-to-nearest, so a CA2 zero never carries a sign (hd(0) = 0).  These run on
+//     the FMA pipe, which the LOP3 stream of the upper levels (ALU pipe) leaves idle.
+//   * alpha[l] (the 2^l LLRs a node receives) for l = 6 .. lsa lives in shared memory, above in a per-warp
+//     workspace, the channel level in the plane buffer written by ss_planes_kernel.  Quad q of chunk c sits at
+//     uint4 index (2c + q) * 32 + lane: conflict-free / coalesced 512-byte rows.  alpha[5] and below never
+//     leave registers.
+//
+// Bit-exactness: CA2 only (SIGMAG stays on decode_bs.cuh: its -0 and tie rules do not map onto IEEE zeros).
+// f / g at n >= 64: bs_arith.cuh.  Inside a 32-LLR node: g saturates at +-(2^(Q-1)-1) (times the static scale)
+// unless the node lies inside the PAR-wide un-saturated leaf decoder (Spec_P*_ext, functions.h:413-546);
+// Spec_P2 (functions.h:367-384) = the leaf() cases below.  All-information nodes are replaced by the hard
+// decision only at n >= 32 and only when no LLR of any frame of the warp is zero (DESIGN.md "why pruning is
+// bit-identical"); inside the fp16x2 walker they are simply decoded.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bs_arith.cuh"
+#include "ss_plan.h"
+
+#ifndef SS_SIDE_UNROLL
+#define SS_SIDE_UNROLL 2  // 1: the (left, right) loops of the fp16x2 walker stay loops (one copy of the 8-LLR routines)
+#endif
+#if SS_SIDE_UNROLL == 1
+#define SS_SIDE_PRAGMA _Pragma("unroll 1")
+#else
+#define SS_SIDE_PRAGMA _Pragma("unroll")
+#endif
+#if defined(__CUDACC__)
+#define SS_DEV __device__ __forceinline__
+#define SS_ANY(x) __any_sync(0xFFFFFFFFu, (x))
+#else
+#define SS_DEV inline
+#define SS_ANY(x) (x)
+#endif
+
+namespace scpd {
+
+struct SsParams {
+    const uint32_t* sched;
+    uint32_t sched_words;  // > 0: every CTA keeps a copy of the schedule in shared memory
+    const uint4* planes;   // channel planes of every 32-frame task (ss_planes_kernel)
+    unsigned long long planes_stride;  // uint4 per task
+    uint32_t* xhat;
+    unsigned long long nframes, ntasks;
+    uint32_t n, log2n, wpf;
+    uint32_t lsa, lwin, win_words;
+    uint32_t sm_stride, sm_beta_off;  // uint4, per warp
+    uint4* ws;
+    unsigned long long ws_stride;  // uint4 per warp
+    uint32_t ws_beta_off;
+    uint32_t aoff[24];
+};
+
+namespace ss {
+
+// ------------------------------------------------------------------------------------------------ fp16x2
+#if defined(__CUDA_ARCH__)
+struct H2 {
+    uint32_t u;
+};
+SS_DEV H2 h2_add(H2 a, H2 b) {
+    H2 r;
+    asm("add.f16x2 %0, %1, %2;" : "=r"(r.u) : "r"(a.u), "r"(b.u));
+    return r;
+}
+SS_DEV H2 h2_sub(H2 a, H2 b) {
+    H2 r;
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(r.u) : "r"(a.u), "r"(b.u));
+    return r;
+}
+SS_DEV H2 h2_abssub(H2 s, H2 d) {  // |s| - |d|: one HADD2 with operand modifiers
+    uint32_t as, ad;
+    asm("abs.f16x2 %0, %1;" : "=r"(as) : "r"(s.u));
+    asm("abs.f16x2 %0, %1;" : "=r"(ad) : "r"(d.u));
+    H2 r;
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(r.u) : "r"(as), "r"(ad));
+    return r;
+}
+SS_DEV H2 h2_fma(H2 a, H2 b, H2 c) {
+    H2 r;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r.u) : "r"(a.u), "r"(b.u), "r"(c.u));
+    return r;
+}
+SS_DEV H2 h2_mul(H2 a, H2 b) {
+    H2 r;
+    asm("mul.f16x2 %0, %1, %2;" : "=r"(r.u) : "r"(a.u), "r"(b.u));
+    return r;
+}
+// half bits of v * 2^-24 (v < 2^11 << k, at most 11 significant bits)
+__host__ __device__ constexpr uint32_t h_bits(uint32_t v) {
+    if (v < 1024u) return v;  // denormal
+    int e = 0;
+    for (uint32_t t = v; t > 1u; t >>= 1) e++;
+    const uint32_t mant = (e >= 10 ? (v >> (e - 10)) : (v << (10 - e))) & 0x3FFu;
+    return ((uint32_t)(e - 9) << 10) | mant;
+}
+template <uint32_t V>
+SS_DEV H2 h2_clamp(H2 x) {  // to +-V (units of 2^-24)
+    constexpr uint32_t hb = h_bits(V), pos = hb | (hb << 16), neg = pos | 0x80008000u;
+    H2 r;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r.u) : "r"(x.u), "r"(neg));
+    asm("min.f16x2 %0, %1, %2;" : "=r"(r.u) : "r"(r.u), "r"(pos));
+    return r;
+}
+SS_DEV H2 h2_one() { return H2{0x3C003C00u}; }
+SS_DEV H2 h2_half() { return H2{0x38003800u}; }
+SS_DEV H2 h2_sumboth(H2 a) {  // (lo + hi) in both halves
+    H2 sw{__byte_perm(a.u, a.u, 0x1032)};
+    return h2_add(a, sw);
+}
+SS_DEV H2 h2_sgn(H2 a) { return H2{bs::lop3<((bs::LA & bs::LB) | bs::LC) & 0xFFu>(a.u, 0x80008000u, 0x3C003C00u)}; }
+SS_DEV H2 h2_xorsgn(H2 a) {  // (sign(lo) ^ sign(hi) as +-1, +1)
+    const uint32_t t = a.u ^ (a.u >> 16);
+    return H2{(t & 0x8000u) | 0x3C003C00u};
+}
+// sign-magnitude bytes (s << 7 | mag): byte c of wa -> low half, byte c of wb -> high half
+SS_DEV H2 h2_from_sm(uint32_t wa, uint32_t wb, int c) {  // c folds to an immediate selector after unrolling
+    const uint32_t sel = (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
+    return H2{__byte_perm(wa, wb, sel) & 0x807F807Fu};
+}
+// sign bits of 16 registers of +-1.0 pairs -> one word, bit 2j = low half of B[j]
+SS_DEV uint32_t h2_pack16(const H2 (&B)[16]) {
+    uint32_t acc = 0u;
+#pragma unroll
+    for (int j = 15; j >= 0; j--) {
+        // (B - 0x3C003C00) has the two sign bits at 15 and 31; times (1 + 2^15) brings them to 30 and 31
+        const uint32_t y = B[j].u * 0x8001u - 0x3C003C00u * 0x8001u;
+        acc = __funnelshift_l(y, acc, 2);
+    }
+    return acc;
+}
+#else
+struct H2 {
+    float lo, hi;
+};
+SS_DEV H2 h2_add(H2 a, H2 b) { return H2{a.lo + b.lo, a.hi + b.hi}; }
+SS_DEV H2 h2_sub(H2 a, H2 b) { return H2{a.lo - b.lo, a.hi - b.hi}; }
+SS_DEV float h2_fabs(float x) { return x < 0 ? -x : (x == 0 ? 0.f : x); }
+SS_DEV H2 h2_abssub(H2 s, H2 d) { return H2{h2_fabs(s.lo) - h2_fabs(d.lo), h2_fabs(s.hi) - h2_fabs(d.hi)}; }
+SS_DEV H2 h2_fma(H2 a, H2 b, H2 c) { return H2{a.lo * b.lo + c.lo, a.hi * b.hi + c.hi}; }
+SS_DEV H2 h2_mul(H2 a, H2 b) { return H2{a.lo * b.lo, a.hi * b.hi}; }
+template <uint32_t V>
+SS_DEV H2 h2_clamp(H2 x) {
+    const float m = (float)V;
+    auto c = [m](float v) { return v > m ? m : (v < -m ? -m : v); };
+    return H2{c(x.lo), c(x.hi)};
+}
+SS_DEV H2 h2_one() { return H2{1.f, 1.f}; }
+SS_DEV H2 h2_half() { return H2{0.5f, 0.5f}; }
+SS_DEV H2 h2_sumboth(H2 a) { return H2{a.lo + a.hi, a.lo + a.hi}; }
+SS_DEV bool h2_neg(float x) { return __builtin_signbit(x) != 0; }
+SS_DEV H2 h2_sgn(H2 a) { return H2{h2_neg(a.lo) ? -1.f : 1.f, h2_neg(a.hi) ? -1.f : 1.f}; }
+SS_DEV H2 h2_xorsgn(H2 a) { return H2{h2_neg(a.lo) != h2_neg(a.hi) ? -1.f : 1.f, 1.f}; }
+SS_DEV H2 h2_from_sm(uint32_t wa, uint32_t wb, int c) {
+    const uint32_t a = (wa >> (8 * c)) & 0xFFu, b = (wb >> (8 * c)) & 0xFFu;
+    auto v = [](uint32_t x) { const float m = (float)(x & 0x7Fu); return (x & 0x80u) ? -m : m; };
+    return H2{v(a), v(b)};
+}
+SS_DEV uint32_t h2_pack16(const H2 (&B)[16]) {
+    uint32_t acc = 0u;
+    for (int j = 0; j < 16; j++) acc |= (h2_neg(B[j].lo) ? 1u : 0u) << (2 * j) | (h2_neg(B[j].hi) ? 1u : 0u) << (2 * j + 1);
+    return acc;
+}
+#endif
+
+// 8 rows x 32 columns of bits, seen as four 8 x 8 matrices (one per byte column): transpose each of them.
+// in: row p bit (8c + k);  out: row k byte c bit p.  Three delta-swap stages.
+SS_DEV void transpose8x8x4(uint32_t (&w)[8]) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const uint32_t t = ((w[p] >> 4) ^ w[p + 4]) & 0x0F0F0F0Fu;
+        w[p + 4] ^= t;
+        w[p] ^= t << 4;
+    }
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        if (p & 2) continue;
+        const uint32_t t = ((w[p] >> 2) ^ w[p + 2]) & 0x33333333u;
+        w[p + 2] ^= t;
+        w[p] ^= t << 2;
+    }
+#pragma unroll
+    for (int p = 0; p < 8; p += 2) {
+        const uint32_t t = ((w[p] >> 1) ^ w[p + 1]) & 0x55555555u;
+        w[p + 1] ^= t;
+        w[p] ^= t << 1;
+    }
+}
+
+// 32 int8 LLRs of one frame (v[j] = LLRs 4j .. 4j+3, as they lie in memory) -> one chunk of sign-magnitude planes,
+// bit i of every plane = LLR i.                                      wrapper_in.h:30-42, qconv_format scalar.h:229-239
+template <int P>
+SS_DEV void chunk_planes(const uint32_t (&v)[8], bs::Val<P>& x) {
+    // row j of the bit matrix = bytes of the LLRs (j, 8 + j, 16 + j, 24 + j): LLR s is byte s % 4 of word s / 4
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t b = j & 3, sel = b | ((4u + b) << 4);
+        const uint32_t t0 = bs::bperm(v[j / 4], v[2 + j / 4], sel), t1 = bs::bperm(v[4 + j / 4], v[6 + j / 4], sel);
+        w[j] = bs::bperm(t0, t1, 0x5410);
+    }
+    transpose8x8x4(w);  // w[b] bit i = bit b of LLR i (two's complement)
+    bs::from_int8_planes<P>(w, x);
+}
+
+// The fp16x2 walker of a node of 32 LLRs and everything below it.  Register j of an array holds the LLRs
+// (2j, 2j+1) of the node, so the pair (i, i + n/2) of a node of n >= 4 is (register i/2, register i/2 + n/4):
+// every op is a full-width fp16x2 op; only the 2-LLR terminals look inside a register.
+//
+// Nodes of 8 LLRs are decoded by straight-line routines specialised at compile time for the information-flag
+// patterns that polar constructions produce (nine 8-bit patterns cover all 47 frozen tables of the reference:
+// ss_plan.h, SS_KNOWN8), selected through a jump table; any other pattern (arbitrary flag tables are legal
+// input) runs the same template with the flags read at run time.  The two levels above (16, 32) are loops over
+// (left, right) so that the routines exist once.
+
+// node types of the 7 nodes of an 8-LLR node from its flag byte, local heap order (0: the node, 1-2: the
+// 4-LLR children, 3-6: the 2-LLR terminals)
+template <uint32_t PAT>
+struct CtDesc8 {
+    template <int HEAP>
+    SS_HD static constexpr uint32_t tp() {
+        if (HEAP == 0) return PAT == 0u ? SS_T_R0 : SS_T_MIX;
+        if (HEAP <= 2) return ((PAT >> (4 * (HEAP >= 1 ? HEAP - 1 : 0))) & 15u) == 0u ? SS_T_R0 : SS_T_MIX;
+        const uint32_t f = (PAT >> (2 * (HEAP >= 3 ? HEAP - 3 : 0))) & 3u;  // f0 | f1 << 1
+        return f == 2u ? 0u : f == 0u ? 1u : f == 3u ? 2u : 3u;  // (0,1) (0,0) (1,1) (1,0)
+    }
+};
+struct RtDesc8 {
+    uint32_t fb;     // flag byte
+    uint32_t prune;  // 0: all-frozen nodes are decoded like any other (pruning mode NONE)
+    template <int HEAP>
+    SS_DEV uint32_t tp() const {
+        if (HEAP == 0) return (prune && fb == 0u) ? SS_T_R0 : SS_T_MIX;
+        if (HEAP <= 2) return (prune && ((fb >> (4 * (HEAP >= 1 ? HEAP - 1 : 0))) & 15u) == 0u) ? SS_T_R0 : SS_T_MIX;
+        const uint32_t f = (fb >> (2 * (HEAP >= 3 ? HEAP - 3 : 0))) & 3u;
+        return f == 2u ? 0u : f == 0u ? 1u : f == 3u ? 2u : 3u;
+    }
+};
+
+template <int Q, int LOG2PAR, bool EXT>
+struct Walk {
+    static constexpr int P = Q - 1;
+    static constexpr uint32_t MAXV = (1u << (Q - 1)) - 1u;
+    // g of a node of n LLRs saturates unless the node lies inside the un-saturated PAR-wide leaf decoder
+    SS_HD static constexpr bool sat(int n) { return !(EXT && n <= (1 << LOG2PAR)); }
+    // f doubles the scale (2 f = |a+b| - |a-b|).  Where a saturating g follows further down the scale must be
+    // known, so there f is halved again (one more HMUL2); elsewhere the factor rides along (f, g, hd are homogeneous)
+    SS_HD static constexpr bool halve(int n) { return n >= 8 && sat(n / 2); }
+
+    static SS_DEV H2 f2(H2 a, H2 b) { return h2_abssub(h2_add(a, b), h2_sub(a, b)); }  // F_function_C2 functions.h:48-61
+
+    // N <= 8 LLRs in A (scale 2^SC), node HEAP of the descriptor D; B = partial sums as +-1.0 (-1 = bit 1)
+    template <int N, int HEAP, int SC, class D>
+    static SS_DEV void node(const H2 (&A)[N / 2], const D& d, H2 (&B)[N / 2]) {
+        const uint32_t t = d.template tp<HEAP>();
+        if constexpr (N == 2) {  // Spec_P2, functions.h:367-384 with F_simplified / G_simplified :90-118
+            if (t == 1u)
+                B[0] = h2_one();  // (0,0)
+            else if (t == 2u)
+                B[0] = h2_sgn(A[0]);  // (1,1): (u0 ^ u1, u1) = (hd(a), hd(b)) for every input
+            else if (t == 0u)
+                B[0] = h2_sgn(h2_sumboth(A[0]));  // (0,1): u1 = sign of the exact sum, sum 0 -> 0
+            else
+                B[0] = h2_xorsgn(A[0]);  // (1,0)
+        } else {
+            constexpr int H = N / 4;  // registers per half
+            if (t == SS_T_R0) {
+#pragma unroll
+                for (int i = 0; i < 2 * H; i++) B[i] = h2_one();
+                return;
+            }
+            const uint32_t tl = d.template tp<2 * HEAP + 1>(), tr = d.template tp<2 * HEAP + 2>();
+            H2 BL[H], BR[H];
+            if (tl != SS_T_R0) {
+                H2 AL[H];
+#pragma unroll
+                for (int i = 0; i < H; i++) AL[i] = f2(A[i], A[i + H]);
+                node<N / 2, 2 * HEAP + 1, SC + 1>(AL, d, BL);
+            }
+            if (tr != SS_T_R0) {
+                H2 AR[H];
+#pragma unroll
+                for (int i = 0; i < H; i++) {  // g = b + (1 - 2u) a                    G_function_C2 functions.h:63-88
+                    AR[i] = tl != SS_T_R0 ? h2_fma(A[i], BL[i], A[i + H]) : h2_add(A[i], A[i + H]);
+                    if constexpr (sat(N)) AR[i] = h2_clamp<(MAXV << SC)>(AR[i]);  // qsat scalar.h:15-21
+                }
+                node<N / 2, 2 * HEAP + 2, SC>(AR, d, BR);
+            }
+#pragma unroll
+            for (int i = 0; i < H; i++) {  // H_STATE my_module.h:903-932: (left ^ right, right)
+                if (tl == SS_T_R0) {
+                    B[i] = tr != SS_T_R0 ? BR[i] : h2_one();
+                } else {
+                    B[i] = tr != SS_T_R0 ? h2_mul(BL[i], BR[i]) : BL[i];
+                }
+                B[i + H] = tr != SS_T_R0 ? BR[i] : h2_one();
+            }
+        }
+    }
+    template <uint32_t PAT>
+    static SS_DEV void node8c(const H2 (&A)[4], H2 (&B)[4]) {
+        node<8, 0, 0>(A, CtDesc8<PAT>(), B);
+    }
+    // id: index into SS_KNOWN8 (ss_plan.h), anything else: the flags at run time
+    static SS_DEV void dispatch8(uint32_t id, uint32_t fb, uint32_t prune, const H2 (&A)[4], H2 (&B)[4]) {
+        switch (id) {
+            case 1: node8c<0xFFu>(A, B); break;
+            case 2: node8c<0xFEu>(A, B); break;
+            case 3: node8c<0xE8u>(A, B); break;
+            case 4: node8c<0x80u>(A, B); break;
+            case 5: node8c<0xE0u>(A, B); break;
+            case 6: node8c<0xFCu>(A, B); break;
+            case 7: node8c<0xF8u>(A, B); break;
+            case 8: node8c<0xC0u>(A, B); break;
+            default: node<8, 0, 0>(A, RtDesc8{fb, prune}, B); break;
+        }
+    }
+    // 16 LLRs (scale 1); ids / fl: pattern ids (4 bits each) and flag bytes of the two 8-LLR children
+    static SS_DEV void walk16(const H2 (&A)[8], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[8]) {
+        H2 BL[4], Bc[4];
+SS_SIDE_PRAGMA
+        for (int side = 0; side < 2; side++) {
+            const uint32_t id = (ids >> (4 * side)) & 15u, fb = (fl >> (8 * side)) & 255u;
+            if (id != 0u) {
+                H2 A8[4];
+                if (side == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        A8[i] = f2(A[i], A[i + 4]);
+                        if constexpr (halve(16)) A8[i] = h2_mul(A8[i], h2_half());
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {  // BL = +1 where the left child is all-frozen
+                        A8[i] = h2_fma(A[i], BL[i], A[i + 4]);
+                        if constexpr (sat(16)) A8[i] = h2_clamp<MAXV>(A8[i]);
+                    }
+                }
+                dispatch8(id, fb, prune, A8, Bc);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) Bc[i] = h2_one();
+            }
+            if (side == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) BL[i] = Bc[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            B[i] = h2_mul(BL[i], Bc[i]);
+            B[i + 4] = Bc[i];
+        }
+    }
+    // 32 LLRs (scale 1); ids: four pattern ids, fl: the 32 information flags
+    static SS_DEV void walk32(const H2 (&A)[16], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[16]) {
+        H2 BL[8], Bc[8];
+SS_SIDE_PRAGMA
+        for (int side = 0; side < 2; side++) {
+            const uint32_t id2 = (ids >> (8 * side)) & 255u, fl2 = (fl >> (16 * side)) & 0xFFFFu;
+            if (id2 != 0u) {
+                H2 A16[8];
+                if (side == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        A16[i] = f2(A[i], A[i + 8]);
+                        if constexpr (halve(32)) A16[i] = h2_mul(A16[i], h2_half());
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        A16[i] = h2_fma(A[i], BL[i], A[i + 8]);
+                        if constexpr (sat(32)) A16[i] = h2_clamp<MAXV>(A16[i]);
+                    }
+                }
+                walk16(A16, id2, fl2, prune, Bc);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) Bc[i] = h2_one();
+            }
+            if (side == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) BL[i] = Bc[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            B[i] = h2_mul(BL[i], Bc[i]);
+            B[i + 8] = Bc[i];
+        }
+    }
+
+    // one chunk of sign-magnitude planes -> 16 fp16x2 registers
+    static SS_DEV void to_h2(const bs::Val<P>& r, H2 (&A)[16]) {
+        uint32_t w[8];
+#pragma unroll
+        for (int p = 0; p < 7; p++) w[p] = p < P ? r.m[p] : 0u;
+        w[7] = r.s & bs::nonzero<P>(r);  // a CA2 zero carries no sign
+        transpose8x8x4(w);  // w[k] byte c = LLR 8c + k as (s << 7 | mag)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            A[4 * c + 0] = h2_from_sm(w[0], w[1], c);
+            A[4 * c + 1] = h2_from_sm(w[2], w[3], c);
+            A[4 * c + 2] = h2_from_sm(w[4], w[5], c);
+            A[4 * c + 3] = h2_from_sm(w[6], w[7], c);
+        }
+    }
+};
+
+}  // namespace ss
+
+// A node of 32 LLRs given as one chunk of planes -> its 32 partial sums.  t: node type; fl: its 32 information
+// flags; ids: pattern ids of its four 8-LLR nodes (0 = all-frozen and pruned); prune: pruning mode != NONE.
+template <int Q, int LOG2PAR, bool EXT>
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+inline
+#endif
+uint32_t ss_sub32(uint32_t s, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4, uint32_t m5, uint32_t m6,
+                  uint32_t t, uint32_t fl, uint32_t ids, uint32_t prune) {
+    constexpr int P = Q - 1;
+    using W = ss::Walk<Q, LOG2PAR, EXT>;
+    bs::Val<P> r;
+    r.s = s;
+    const uint32_t m[7] = {m0, m1, m2, m3, m4, m5, m6};
+#pragma unroll
+    for (int k = 0; k < P; k++) r.m[k] = m[k];
+    if (t == SS_T_R1) {
+        const uint32_t nz = bs::nonzero<P>(r);
+        if (!SS_ANY(~nz != 0u)) return r.s;  // no zero anywhere in the warp: nz is all ones, hd = sign
+    }
+    ss::H2 A[16], B[16];
+    W::to_h2(r, A);
+    W::walk32(A, ids, fl, prune, B);
+    return ss::h2_pack16(B);
+}
+
+// One lane's view of the decoder state.  All pointers already include the lane.
+template <int Q, int LOG2PAR, bool EXT>
+struct SsThread {
+    static constexpr int P = Q - 1;
+    static constexpr int FMT = bs::FMT_CA2;
+    using V = bs::Val<P>;
+    using W = ss::Walk<Q, LOG2PAR, EXT>;
+    static_assert(Q >= 5 && Q <= 8, "two quads per chunk");
+    static_assert(LOG2PAR <= 5, "the un-saturated leaf decoder must sit inside a 32-LLR node");
+
+    const SsParams& p;
+    uint4* sm;          // the warp's shared region + lane
+    uint4* wsl;         // the warp's workspace + lane
+    const uint4* pl;    // channel planes of the current task + lane
+    const uint32_t* sched;  // shared copy or global
+
+    SS_DEV SsThread(const SsParams& p_) : p(p_) {}
+
+    SS_DEV uint4* aptr(uint32_t l) const {
+        if (l == p.log2n) return const_cast<uint4*>(pl);
+        return (l <= p.lsa ? sm : wsl) + p.aoff[l];
+    }
+    // partial sums of node level l, word w: component w & 3 of a quad
+    SS_DEV uint4* bquad(uint32_t l, uint32_t w) const {
+        if (l < p.lwin) return sm + p.sm_beta_off + (((w & (p.win_words - 1u)) >> 2) * 32u);
+        return wsl + p.ws_beta_off + ((w >> 2) * 32u);
+    }
+    SS_DEV uint32_t* bword(uint32_t l, uint32_t w) const { return reinterpret_cast<uint32_t*>(bquad(l, w)) + (w & 3u); }
+
+    static SS_DEV void load(const uint4* q, V& x) {
+        const uint4 a = q[0], b = q[32];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        x.s = w[0];
+#pragma unroll
+        for (int k = 0; k < P; k++) x.m[k] = w[1 + k];
+    }
+    static SS_DEV void store(uint4* q, const V& x) {
+        uint32_t w[8];
+        w[0] = x.s;
+#pragma unroll
+        for (int k = 1; k < 8; k++) w[k] = k <= P ? x.m[k - 1] : 0u;
+        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        q[32] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+
+    // ---------------------------------------------------------------- nodes of 128 LLRs and more
+    // alpha[l-1] chunk c = f(alpha[l] chunk c, chunk c + half)                   F_STATE my_module.h:373-445
+    SS_DEV void op_f(uint32_t l) {
+        const uint4* src = aptr(l);
+        uint4* dst = aptr(l - 1);
+        const uint32_t half = 1u << (l - 6);
+        for (uint32_t c = 0; c < half; c += 2) {
+            V a0, b0, a1, b1, r0, r1;
+            load(src + c * 64u, a0);
+            load(src + (c + half) * 64u, b0);
+            load(src + (c + 1u) * 64u, a1);
+            load(src + (c + 1u + half) * 64u, b1);
+            bs::f_op<P>(a0, b0, r0);
+            bs::f_op<P>(a1, b1, r1);
+            store(dst + c * 64u, r0);
+            store(dst + (c + 1u) * 64u, r1);
+        }
+    }
+    // alpha[l-1] = g(alpha[l], beta of the left child); zero: left child all-frozen   G_STATE my_module.h:704-781
+    SS_DEV void op_g(uint32_t l, uint32_t wd, bool zero) {
+        const uint4* src = aptr(l);
+        uint4* dst = aptr(l - 1);
+        const uint32_t half = 1u << (l - 6);
+        for (uint32_t c = 0; c < half; c += 2) {
+            V a0, b0, a1, b1, r0, r1;
+            load(src + c * 64u, a0);
+            load(src + (c + half) * 64u, b0);
+            load(src + (c + 1u) * 64u, a1);
+            load(src + (c + 1u + half) * 64u, b1);
+            uint2 u = make_uint2(0u, 0u);
+            if (!zero) u = *reinterpret_cast<const uint2*>(bword(l - 1, wd + c));
+            bs::g_sat_ca2<P>(a0, b0, u.x, r0);
+            bs::g_sat_ca2<P>(a1, b1, u.y, r1);
+            store(dst + c * 64u, r0);
+            store(dst + (c + 1u) * 64u, r1);
+        }
+    }
+    // node (l, wd) := (left ^ right, right); copy: the left child is all-frozen      H_STATE my_module.h:903-932
+    SS_DEV void op_h(uint32_t l, uint32_t wd, bool copy) {
+        const uint32_t nw = 1u << (l - 6);  // words per half
+        if (nw == 2u) {  // l = 7: the node is one quad, always inside the window
+            uint4* q = bquad(7, wd);
+            uint4 x = *q;
+            if (copy) {
+                x.x = x.z;
+                x.y = x.w;
+            } else {
+                x.x ^= x.z;
+                x.y ^= x.w;
+            }
+            *q = x;
+            return;
+        }
+        const bool move = (l - 1 < p.lwin) != (l < p.lwin);  // children in the window, the node in the workspace
+        for (uint32_t i = 0; i < nw; i += 4) {
+            uint4 x = *bquad(l - 1, wd + nw + i);
+            if (move) *bquad(l, wd + nw + i) = x;
+            if (!copy) {
+                const uint4 y = *bquad(l - 1, wd + i);
+                x.x ^= y.x;
+                x.y ^= y.y;
+                x.z ^= y.z;
+                x.w ^= y.w;
+            }
+            *bquad(l, wd + i) = x;
+        }
+    }
+    SS_DEV void op_r0(uint32_t l, uint32_t wd) {
+        if (l == 6u) {
+            *reinterpret_cast<uint2*>(bword(6, wd)) = make_uint2(0u, 0u);
+            return;
+        }
+        const uint32_t nw = 1u << (l - 5);
+        for (uint32_t i = 0; i < nw; i += 4) *bquad(l, wd + i) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // hard decision of alpha[l]; returns true (warp-uniform) when some LLR of some frame is zero
+    SS_DEV bool op_hd(uint32_t l, uint32_t wd) {
+        const uint4* src = aptr(l);
+        const uint32_t nc = 1u << (l - 5);
+        uint32_t z = 0u;
+        for (uint32_t c = 0; c < nc; c += 4) {
+            uint32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                V a;
+                load(src + (c + k) * 64u, a);
+                const uint32_t nz = bs::nonzero<P>(a);
+                z |= ~nz;
+                x[k] = a.s & nz;
+            }
+            *bquad(l, wd + c) = make_uint4(x[0], x[1], x[2], x[3]);
+        }
+        return SS_ANY(z != 0u);
+    }
+
+    // ---------------------------------------------------------------- nodes of 64 and 32 LLRs
+    // partial-sum word of a node of 32 LLRs given as one chunk of planes (out of line: one copy of the walker)
+    SS_DEV uint32_t sub32(const V& r, uint32_t t, uint32_t fl, uint32_t ids, uint32_t prune) {
+        uint32_t m[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) m[k] = k < P ? r.m[k] : 0u;
+        return ss_sub32<Q, LOG2PAR, EXT>(r.s, m[0], m[1], m[2], m[3], m[4], m[5], m[6], t, fl, ids, prune);
+    }
+    // a, b: the two chunks of alpha[6] (also stored at aptr(6) when the node needs them again for g)
+    // d0: node types (64, left 32, right 32) + kind + pruning flag; d1: the 64 flags' low word, d2: high word,
+    // d3: pattern ids of the eight 8-LLR nodes (4 bits each)
+    SS_DEV void sub64(uint32_t wd, const V& a, const V& b, bool stored, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3) {
+        const uint32_t t64 = d0 & 3u, tl = (d0 >> 2) & 3u, tr = (d0 >> 4) & 3u, prune = (d0 >> 10) & 1u;
+        uint32_t bl = 0u, br = 0u;
+        bool walk = true;
+        if (t64 == SS_T_R1) {
+            const uint32_t nza = bs::nonzero<P>(a), nzb = bs::nonzero<P>(b);
+            if (!SS_ANY((~nza | ~nzb) != 0u)) {
+                *reinterpret_cast<uint2*>(bword(6, wd)) = make_uint2(a.s, b.s);
+                walk = false;
+            }
+        }
+        if (walk) {
+            if (!stored && tr != SS_T_R0 && tl != SS_T_R0) {
+                store(aptr(6), a);
+                store(aptr(6) + 64, b);
+            }
+            if (tl != SS_T_R0) {
+                V r;
+                bs::f_op<P>(a, b, r);
+                bl = sub32(r, tl, d1, d3 & 0xFFFFu, prune);
+            }
+            if (tr != SS_T_R0) {
+                V r;
+                if (tl != SS_T_R0) {
+                    V a2, b2;  // reloaded: keeping 16 registers alive across the left child costs more
+                    load(aptr(6), a2);
+                    load(aptr(6) + 64, b2);
+                    bs::g_sat_ca2<P>(a2, b2, bl, r);
+                } else {
+                    bs::g_sat_ca2<P>(a, b, 0u, r);
+                }
+                br = sub32(r, tr, d2, d3 >> 16, prune);
+            }
+            *reinterpret_cast<uint2*>(bword(6, wd)) = make_uint2(bl ^ br, br);
+        }
+    }
+    // SS_SUB: the 64-LLR node from alpha[6];  SS_XS: f / g / g0 of the 128-LLR node above, straight into the child
+    SS_DEV void op_sub(uint32_t wd, uint32_t pc, bool xs) {
+        const uint32_t d0 = sched[pc + 1], kind = (d0 >> 8) & 3u;
+        V r0, r1;
+        if (!xs) {
+            load(aptr(6), r0);
+            load(aptr(6) + 64, r1);
+        } else {
+            const uint4* src = aptr(7);
+            V a0, b0, a1, b1;
+            load(src, a0);
+            load(src + 128, b0);
+            load(src + 64, a1);
+            load(src + 192, b1);
+            if (kind == SS_F) {
+                bs::f_op<P>(a0, b0, r0);
+                bs::f_op<P>(a1, b1, r1);
+            } else {
+                uint2 u = make_uint2(0u, 0u);
+                if (kind == SS_G) u = *reinterpret_cast<const uint2*>(bword(6, wd & ~3u));
+                bs::g_sat_ca2<P>(a0, b0, u.x, r0);
+                bs::g_sat_ca2<P>(a1, b1, u.y, r1);
+            }
+        }
+        sub64(wd, r0, r1, !xs, d0, sched[pc + 2], sched[pc + 3], sched[pc + 4]);
+    }
+
+    SS_DEV void run() {
+        uint32_t pc = 0;
+        for (;;) {
+            const uint32_t w = sched[pc];
+            const uint32_t code = ss_op_code(w), l = ss_op_level(w), wd = ss_op_word(w);
+            switch (code) {
+                case SS_END: return;
+                case SS_F:
+                    op_f(l);
+                    pc++;
+                    break;
+                case SS_G:
+                    op_g(l, wd, false);
+                    pc++;
+                    break;
+                case SS_G0:
+                    op_g(l, wd, true);
+                    pc++;
+                    break;
+                case SS_H:
+                    op_h(l, wd, false);
+                    pc++;
+                    break;
+                case SS_HCOPY:
+                    op_h(l, wd, true);
+                    pc++;
+                    break;
+                case SS_R0:
+                    op_r0(l, wd);
+                    pc++;
+                    break;
+                case SS_R1: {
+                    const bool z = op_hd(l, wd);
+                    pc += 2u + (z ? 0u : sched[pc + 1]);
+                    break;
+                }
+                case SS_SUB:
+                case SS_XS:
+                    op_sub(wd, pc, code == SS_XS);
+                    pc += 5;
+                    break;
+                default: return;
+            }
+        }
+    }
+    // the root's partial sums are the packed row of the lane's frame (wrapper_out.h:31-33 laid end to end)
+    SS_DEV void write_output(unsigned long long frame) {
+        if (frame >= p.nframes) return;
+        uint32_t* row = p.xhat + frame * p.wpf;
+        for (uint32_t w = 0; w < p.wpf; w += 4) *reinterpret_cast<uint4*>(row + w) = *bquad(p.log2n, w);
+    }
+};
+
+#if defined(__CUDACC__)
+// int8 rows -> sign-magnitude planes in the chunk layout of the decode kernel.        wrapper_in.h:30-42
+// One warp per (task, 8 chunks); lane = frame: 32 bytes of the lane's row per chunk.
+template <int Q>
+__global__ void __launch_bounds__(256) ss_planes_kernel(const int8_t* __restrict__ llr, unsigned long long nframes, uint32_t n,
+                                                        uint4* __restrict__ planes, unsigned long long planes_stride) {
+    constexpr int P = Q - 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long ntasks = (nframes + 31) / 32;
+    const uint32_t blocks_per_task = n / 256u;  // n >= 256; n = 128 handled by the tail below
+    const unsigned long long nunits = ntasks * (blocks_per_task ? blocks_per_task : 1u);
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < nunits; t += wstride) {
+        const unsigned long long task = blocks_per_task ? t / blocks_per_task : t;
+        const uint32_t c0 = blocks_per_task ? (uint32_t)(t % blocks_per_task) * 8u : 0u;
+        const uint32_t nc = blocks_per_task ? 8u : n / 32u;
+        const unsigned long long f = task * 32ull + lane;
+        const bool valid = f < nframes;
+        const int8_t* row = llr + (valid ? f : 0ull) * n;
+        uint4* dst = planes + task * planes_stride + lane;
+        for (uint32_t c = c0; c < c0 + nc; c++) {
+            uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (valid) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(row + 32u * c));
+                const uint4 y = __ldg(reinterpret_cast<const uint4*>(row + 32u * c) + 1);
+                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+            }
+            bs::Val<P> x;
+            ss::chunk_planes<P>(v, x);
+            uint32_t o[8];
+            o[0] = x.s;
+#pragma unroll
+            for (int k = 1; k < 8; k++) o[k] = k <= P ? x.m[k - 1] : 0u;
+            dst[(2u * c) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[(2u * c + 1u) * 32u] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
+#ifndef SCPD_SS_THREADS
+#define SCPD_SS_THREADS 512  // upper bound of the CTA size: 16 warps, one CTA per SM, up to 128 registers
+#endif
+template <int Q, int LOG2PAR, bool EXT>
+__global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const SsParams p) {
+    extern __shared__ __align__(16) uint4 ss_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    SsThread<Q, LOG2PAR, EXT> t(p);
+    t.sm = ss_smem + (size_t)warp * p.sm_stride + lane;
+    uint32_t* sm_sched = reinterpret_cast<uint32_t*>(ss_smem + (size_t)nwarps * p.sm_stride);
+    if (p.sched_words) {
+        for (uint32_t i = threadIdx.x; i < p.sched_words; i += blockDim.x) sm_sched[i] = __ldg(p.sched + i);
+        __syncthreads();
+        t.sched = sm_sched;
+    } else {
+        t.sched = p.sched;
+    }
+    const unsigned long long slot = (unsigned long long)blockIdx.x * nwarps + warp;
+    t.wsl = p.ws + slot * p.ws_stride + lane;
+    for (unsigned long long task = slot; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {
+        t.pl = p.planes + task * p.planes_stride + lane;
+        t.run();
+        t.write_output(task * 32ull + lane);
+    }
+}
+#endif
+
+}  // namespace scpd

@@ -18,6 +18,7 @@
 #include "decode_fast.cuh"
 #include "decode_generic.cuh"
 #include "decode_raw.cuh"
+#include "decode_ss.cuh"
 #include "harness.cuh"
 #include "internal.h"
 #include "schedule.h"
@@ -146,6 +147,18 @@ struct scpd_decoder {
     size_t bs_ws_bytes = 0;
     uint8_t* d_bs_planes = nullptr;
     size_t bs_planes_bytes = 0;
+    // slot-sliced kernel plan (decode_ss.cuh): lane = frame; ss_ok == false: not available for this configuration
+    bool ss_ok = false;
+    int ss_warps = 12;
+    bool ss_sched_smem = false;
+    SsPlan ss_plan;
+    std::vector<uint32_t> ss_sched_host;
+    SsStats ss_stats;
+    uint32_t* d_ss_sched = nullptr;
+    uint4* d_ss_ws = nullptr;
+    size_t ss_ws_bytes = 0;
+    uint4* d_ss_planes = nullptr;
+    size_t ss_planes_bytes = 0;
     // raw-pattern kernel plan (decode_raw.cuh): the configurations outside the in-range int16x2 / bit-sliced
     // datapaths.  raw_only: it is the only kernel of this handle
     bool raw_ok = false, raw_only = false;
@@ -255,6 +268,54 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
 #endif
 #undef BS_K
     return nullptr;
+}
+
+typedef void (*ss_kernel_t)(const SsParams);
+// Instantiated (LLR_BITS, log2 PAR, EXTENDED) combinations of the slot-sliced kernel (CA2 only).
+static ss_kernel_t ss_kernel_ptr(int q, int log2par, int ext) {
+#define SS_K(Q, LP, E) \
+    if (q == Q && log2par == LP && ext == (E ? 1 : 0)) return sc_decode_ss_kernel<Q, LP, E>;
+    SS_K(8, 4, true)
+#ifndef SCPD_FAST_BUILD
+    SS_K(8, 4, false)
+    SS_K(7, 4, true)
+    SS_K(6, 4, true)
+    SS_K(6, 4, false)
+    SS_K(8, 2, true)
+    SS_K(8, 3, true)
+    SS_K(7, 5, true)
+    SS_K(6, 5, true)
+#endif
+#undef SS_K
+    return nullptr;
+}
+
+// Decide whether the slot-sliced kernel applies and lay out its shared memory / workspace.
+static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
+    d->ss_ok = false;
+    const char* ksel = std::getenv("SCPD_KERNEL");
+    if (ksel && std::strcmp(ksel, "ss") != 0 && std::strcmp(ksel, "auto") != 0) return SCPD_OK;
+    if (d->cfg.format != SCPD_FMT_CA2 || d->log2n < 7) return SCPD_OK;
+    const int q = (int)d->cfg.llr_bits;
+    // the un-saturated leaf sums must stay exact in fp16 (11 significant bits): (2^(Q-1) - 1) 2^log2PAR <= 2047
+    if (d->cfg.extended && (((1u << (q - 1)) - 1u) << d->log2par) > 2047u) return SCPD_OK;
+    ss_kernel_t k = ss_kernel_ptr(q, d->log2par, (int)d->cfg.extended);
+    if (!k) return SCPD_OK;
+    d->ss_sched_host = ss_build_schedule(d->log2n, (int)d->cfg.pruning, flags, &d->ss_stats, env_int("SCPD_SS_FUSE", 1));
+    d->ss_warps = std::max(1, std::min(SCPD_SS_THREADS / 32, env_int("SCPD_SS_WARPS", SCPD_SS_THREADS / 32)));
+    d->ss_sched_smem = d->ss_sched_host.size() <= (size_t)env_int("SCPD_SS_SCHED_SMEM_WORDS", 2048);
+    const size_t total = (size_t)227 * 1024 - (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
+    const size_t per_warp = std::min<size_t>(total / d->ss_warps, (size_t)env_int("SCPD_SS_SMEM_KB", 1024) * 1024);
+    if (!ss_make_plan(d->log2n, per_warp, &d->ss_plan, env_int("SCPD_SS_LSA", -1), env_int("SCPD_SS_LWIN", -1))) return SCPD_OK;
+    const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * d->ss_warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    d->ss_ok = true;
+    if (env_int("SCPD_VERBOSE", 0))
+        fprintf(stderr, "[scpd] slot-sliced kernel: %d warps/CTA, alpha levels 6..%u and partial sums below level %u in smem, "
+                "%u B/warp, workspace %llu B/warp, %zu schedule words (%s)\n", d->ss_warps, d->ss_plan.lsa, d->ss_plan.lwin,
+                d->ss_plan.sm_stride * 16u, d->ss_plan.ws_stride * 16ull, d->ss_sched_host.size(),
+                d->ss_sched_smem ? "shared" : "global");
+    return SCPD_OK;
 }
 
 // Decide whether the bit-sliced kernel applies and lay out its shared memory / workspace.
@@ -532,6 +593,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
         rc = plan_layout(d);
         if (rc == SCPD_OK) rc = plan_fast(d, flags);
         if (rc == SCPD_OK) rc = plan_bs(d, flags);
+        if (rc == SCPD_OK) rc = plan_ss(d, flags);
         if (rc == SCPD_OK && cfg->format == SCPD_FMT_SIGMAG && !d->bs_ok) d->raw_only = true;
     }
     // SIGMAG handles keep the raw-pattern kernel beside the bit-sliced one for mis-aligned LLR buffers
@@ -565,6 +627,12 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
             e = cudaMemcpy(d->d_bs_sched, d->bs_sched_host.data(), d->bs_sched_host.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && d->ss_ok) {
+        e = cudaMalloc(&d->d_ss_sched, d->ss_sched_host.size() * sizeof(uint32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(d->d_ss_sched, d->ss_sched_host.data(), d->ss_sched_host.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&d->d_counters, 6 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         scpd_destroy(d);
@@ -587,6 +655,9 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_bs_planes);
     cudaFree(d->d_raw_sched);
     cudaFree(d->d_raw_ws);
+    cudaFree(d->d_ss_sched);
+    cudaFree(d->d_ss_ws);
+    cudaFree(d->d_ss_planes);
     for (int b = 0; b < 2; b++) {
         cudaFree(d->d_llr2[b]);
         cudaFree(d->d_xhat2[b]);
@@ -719,6 +790,71 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     return SCPD_OK;
 }
 
+static int grow(void** ptr, size_t* have, size_t need, cudaStream_t st) {
+    if (need <= *have) return SCPD_OK;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    CUDA_TRY(cudaMalloc(ptr, need));
+    *have = need;
+    return SCPD_OK;
+}
+
+// slot-sliced kernel: lane = frame, 32 frames per warp ("task")
+static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
+    const unsigned long long ntasks = (nframes + 31) / 32;
+    // warps per CTA: as many as the plan allows once every SM has that many tasks, fewer for small batches
+    const int warps = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)d->ss_warps,
+                                                                                      (ntasks + d->num_sms - 1) / d->num_sms));
+    const unsigned long long grid = std::min<unsigned long long>((unsigned long long)d->num_sms, (ntasks + warps - 1) / warps);
+    int rc = grow((void**)&d->d_ss_ws, &d->ss_ws_bytes, (size_t)(grid * warps * d->ss_plan.ws_stride * 16ull) + 16, st);
+    if (rc) return rc;
+    const size_t pl_stride = ss_planes_quads(d->log2n);
+    rc = grow((void**)&d->d_ss_planes, &d->ss_planes_bytes, (size_t)ntasks * pl_stride * 16, st);
+    if (rc) return rc;
+    {
+        const unsigned long long units = ntasks * std::max<unsigned long long>(1, d->cfg.n / 256u);
+        const unsigned blocks = (unsigned)std::min<unsigned long long>((units + 7) / 8, (unsigned long long)d->num_sms * 32);
+        switch (d->cfg.llr_bits) {
+            case 6: ss_planes_kernel<6><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride); break;
+            case 7: ss_planes_kernel<7><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride); break;
+            default: ss_planes_kernel<8><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride); break;
+        }
+        d->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    SsParams p;
+    p.sched = d->d_ss_sched;
+    p.sched_words = d->ss_sched_smem ? (uint32_t)d->ss_sched_host.size() : 0u;
+    p.planes = d->d_ss_planes;
+    p.planes_stride = pl_stride;
+    p.xhat = d_xhat;
+    p.nframes = nframes;
+    p.ntasks = ntasks;
+    p.n = d->cfg.n;
+    p.log2n = (uint32_t)d->log2n;
+    p.wpf = d->wpf;
+    p.lsa = d->ss_plan.lsa;
+    p.lwin = d->ss_plan.lwin;
+    p.win_words = d->ss_plan.win_words;
+    p.sm_stride = d->ss_plan.sm_stride;
+    p.sm_beta_off = d->ss_plan.sm_beta_off;
+    p.ws = d->d_ss_ws;
+    p.ws_stride = d->ss_plan.ws_stride;
+    p.ws_beta_off = d->ss_plan.ws_beta_off;
+    for (int l = 0; l < 24; l++) p.aoff[l] = d->ss_plan.aoff[l];
+    const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
+    ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
+    k<<<dim3((unsigned)grid), dim3((unsigned)(warps * 32)), smem, st>>>(p);
+    snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_ss_kernel (slot-sliced, lane per frame, %d warps/CTA)", warps);
+    if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SCPD_OK;
+}
+
 static int decode_raw(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
     const unsigned long long f_per_cta = (unsigned long long)d->warps_per_cta * (32 / d->raw_group);
     unsigned long long grid = (nframes + f_per_cta - 1) / f_per_cta;
@@ -768,6 +904,10 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (d->raw_only) return decode_raw(d, d_llr, nframes, d_xhat, st);
+    // The slot-sliced kernel (a lane per frame) is the default for CA2 once the batch gives every SM a few warps
+    if (d->ss_ok && (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0 &&
+        (nframes + 31) / 32 >= (unsigned long long)env_int("SCPD_SS_MIN_TASKS", d->kernel_pinned ? 1 : 2 * d->num_sms))
+        return decode_ss(d, d_llr, nframes, d_xhat, st);
     // One warp walks the tree of a 32-frame group alone, so the bit-sliced kernel needs many groups to fill the
     // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 24 k at N = 4096,
     // 16 k at N = 32768 and 131072, 8 k at N = 2^19) the int16x2 kernel is faster: 2 frames per lane group, and
@@ -927,6 +1067,8 @@ extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
     if (!d) return "";
     if (d->raw_only)
         snprintf(buf, sizeof buf, "sc_decode_raw_kernel (raw W-bit patterns, %d lanes per frame)", d->raw_group);
+    else if (d->ss_ok)
+        snprintf(buf, sizeof buf, "sc_decode_ss_kernel (slot-sliced, lane per frame, %d warps/CTA)", d->ss_warps);
     else if (d->bs_ok)
         snprintf(buf, sizeof buf, "sc_decode_bs_kernel (bit-sliced, %d lanes per 32-frame group, %d warps/CTA)", d->bs_group,
                  d->bs_warps);

@@ -1,0 +1,112 @@
+// ss_emu.cpp -- TEST INFRASTRUCTURE.  Runs the product's slot-sliced decode kernel source (csrc/decode_ss.cuh,
+// compiled as plain C++ through tests/emu/fake_cuda/cuda_runtime.h) on the CPU.  Every lane of that kernel owns
+// one frame and shares nothing with its neighbours but the schedule, so the emulation is a loop over lanes; the
+// warp vote of the all-information shortcut degenerates to the lane's own flag (both branches give the same bits,
+// which is what the tests check) unless `vote` asks for the whole-warp OR, computed here in a first pass.
+// fp16x2 arithmetic is emulated with exact float pairs (decode_ss.cuh, host branch).  Never a decode path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "cuda_runtime.h"
+// keep this include after the fake runtime
+#include "../../sc_polar_decoder_hls_b200/csrc/decode_ss.cuh"
+
+namespace cuda_emu {
+thread_local LaneCtx* cur = nullptr;
+uint32_t collective_exchange(uint32_t v, int) { return v; }
+uint32_t collective_ballot(bool p) { return p ? 1u : 0u; }
+void collective_sync() {}
+int cta_barrier_or(int p) { return p; }
+}  // namespace cuda_emu
+
+using namespace scpd;
+
+template <int Q, int LOG2PAR, bool EXT>
+static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, size_t nframes, uint32_t* xhat,
+               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats) {
+    constexpr int P = Q - 1;
+    const uint32_t n = 1u << log2n;
+    SsStats st;
+    const std::vector<uint32_t> sched = ss_build_schedule(log2n, pruning, flags, &st, fuse);
+    if (stats) {
+        stats[0] = st.n_ops;
+        stats[1] = st.n_f;
+        stats[2] = st.n_g;
+        stats[3] = st.n_sub32_mixed;
+    }
+    SsPlan plan;
+    if (!ss_make_plan(log2n, smem_per_warp, &plan, force_lsa, force_lwin)) return 1;
+    const size_t ntasks = (nframes + 31) / 32;
+    const size_t pl_stride = ss_planes_quads(log2n);
+    std::vector<uint4> planes(ntasks * pl_stride, uint4{0, 0, 0, 0});
+    // ss_planes_kernel, lane by lane
+    for (size_t f = 0; f < nframes; f++) {
+        uint4* dst = planes.data() + (f / 32) * pl_stride + (f % 32);
+        for (uint32_t c = 0; c < n / 32; c++) {
+            uint32_t v[8];
+            std::memcpy(v, llr + f * n + 32u * c, 32);
+            bs::Val<P> x;
+            ss::chunk_planes<P>(v, x);
+            uint32_t o[8];
+            o[0] = x.s;
+            for (int k = 1; k < 8; k++) o[k] = k <= P ? x.m[k - 1] : 0u;
+            dst[(2u * c) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[(2u * c + 1u) * 32u] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    SsParams p;
+    std::memset(&p, 0, sizeof p);
+    p.sched = sched.data();
+    p.sched_words = 0;
+    p.planes = planes.data();
+    p.planes_stride = pl_stride;
+    p.xhat = xhat;
+    p.nframes = nframes;
+    p.ntasks = ntasks;
+    p.n = n;
+    p.log2n = (uint32_t)log2n;
+    p.wpf = n / 32;
+    p.lsa = plan.lsa;
+    p.lwin = plan.lwin;
+    p.win_words = plan.win_words;
+    p.sm_stride = plan.sm_stride;
+    p.sm_beta_off = plan.sm_beta_off;
+    p.ws_stride = plan.ws_stride;
+    p.ws_beta_off = plan.ws_beta_off;
+    for (int l = 0; l < 24; l++) p.aoff[l] = plan.aoff[l];
+    std::vector<uint4> smem(plan.sm_stride, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    std::vector<uint4> ws(plan.ws_stride ? plan.ws_stride : 1, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    p.ws = ws.data();
+    for (size_t task = 0; task < ntasks; task++) {
+        for (int lane = 0; lane < 32; lane++) {
+            SsThread<Q, LOG2PAR, EXT> t(p);
+            t.sm = smem.data() + lane;
+            t.wsl = ws.data() + lane;
+            t.sched = sched.data();
+            t.pl = planes.data() + task * pl_stride + lane;
+            t.run();
+            t.write_output(task * 32ull + lane);
+        }
+    }
+    return 0;
+}
+
+extern "C" int ss_emu_decode(int log2n, int q, int log2par, int ext, int pruning, const uint8_t* flags, const int8_t* llr,
+                             size_t nframes, uint32_t* xhat, size_t smem_per_warp, int force_lsa, int force_lwin, int fuse,
+                             uint64_t* stats) {
+#define SS_CASE(Q, LP, E)                          \
+    if (q == Q && log2par == LP && ext == (E ? 1 : 0)) \
+        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats);
+    SS_CASE(8, 4, true)
+    SS_CASE(8, 4, false)
+    SS_CASE(6, 4, true)
+    SS_CASE(7, 4, true)
+    SS_CASE(8, 2, true)
+    SS_CASE(8, 5, true)
+    SS_CASE(8, 3, true)
+    SS_CASE(6, 2, false)
+#undef SS_CASE
+    return 2;
+}
