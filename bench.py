@@ -1,20 +1,24 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the SC polar decode path (BASELINE.json metric).
 
-Workload (N=1 and every N): BASELINE.json configs[1] -- N=4096, K=3072
-(Generated_Frozen_Bit/frozen_n_4096_k_3072), 2^20 frames per GPU per step, plain-SC results
-(CA2, LLR_BITS=8, PAR=16, EXTENDED=1; all-frozen / all-information subtrees skipped where that is
-bit-identical), all-zero codeword through the device BPSK/AWGN/quantiser chain at Eb/N0 = 3.5 dB.
+Headline workload (N=1 and every N): BASELINE.json configs[1] -- N=4096, K=3072
+(Generated_Frozen_Bit/frozen_n_4096_k_3072), 2^20 frames per GPU per step, CA2, LLR_BITS=8, PAR=16, EXTENDED=1,
+pruning mode R0+R1 (all-frozen / all-information subtrees skipped where that is proven bit-identical to plain SC:
+DESIGN.md section 2), all-zero codeword through the device BPSK/AWGN/quantiser chain at Eb/N0 = 3.5 dB.
 A "step" is one scpd_decode() over the resident 4 GiB LLR batch (far larger than the 126 MB L2).
 
-  value  : information-bit Gb/s with the LLRs already in HBM (device-timed, CUDA events)
-  e2e    : the same through scpd_decode_host(): pinned host LLRs -> H2D -> decode -> D2H, every step
-  N > 1  : frames are sharded across ranks (one process per GPU, torchrun); no data-path collective,
-           only a barrier and a max-reduction of the elapsed time ("weak" scaling).
+  value    : information-bit Gb/s with the LLRs already in HBM (device-timed, CUDA events)
+  e2e      : the same through scpd_decode_host(): pinned host LLRs -> H2D -> decode -> D2H, every step
+  configs  : (N = 1 only) the same device-resident measurement for all five BASELINE configs c1..c5, each with its own
+             parity spot check against the oracle and both rooflines of SURVEY 8d (bytes at HBM peak, ops at the
+             measured integer-pipe peak)
+  pipeline : (N = 1 only) information Gb/s of the whole device Monte-Carlo loop scpd_run_ber (channel + decode + count)
+  N > 1    : frames are sharded across ranks (one process per GPU, torchrun); no data-path collective,
+             only a barrier and a max-reduction of the elapsed time ("weak" scaling).
 
-`--impl reference` times the reference's own CPU decoder (oracle/_ref, i.e. src/module/my_module.h
-compiled natively; the oracle port if that library is absent) on the host cores for the same
-workload, on a bounded sample.
+`--impl reference` times the reference's own CPU decoder (oracle/_ref, i.e. src/module/my_module.h compiled natively;
+the oracle port if that library is absent) on the host cores for the headline workload, on a bounded sample.  It runs
+the full un-pruned tree (the reference FSM at PRUNING_LEVEL 0); the results are the same bits.
 """
 import argparse
 import ctypes
@@ -31,9 +35,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CFG = dict(name="frozen_n_4096_k_3072", n=4096, k=3072, ebn0=3.5, frames=1 << 20, par=16, llr_bits=8)
+# BASELINE.json configs: table, N, K, Eb/N0, frames per step of the device-resident measurement
+CONFIGS = {
+    "c1": dict(name="FB_N1024_K512", n=1024, k=512, ebn0=2.5, frames=1 << 20, check=256),
+    "c2": dict(name="frozen_n_4096_k_3072", n=4096, k=3072, ebn0=3.5, frames=1 << 20, check=256),
+    "c3": dict(name="frozen_n_32768_k_29492_snr_4_5", n=32768, k=29492, ebn0=4.5, frames=1 << 17, check=64),
+    "c4": dict(name="frozen_n_131072_k_117964", n=131072, k=117964, ebn0=4.5, frames=1 << 15, check=16),
+    "c5": dict(name="frozen_n_524288_k_262144", n=524288, k=262144, ebn0=2.0, frames=1 << 14, check=4),
+}
+HEAD = "c2"
+CFG = dict(CONFIGS[HEAD], par=16, llr_bits=8)
 METRIC = "info-bit Gb/s decoded (bit-exact)"
 UNIT = "Gb/s"
+WORKLOAD = ("BASELINE configs[1]: N=4096 K=3072, 2^20 frames per GPU per step, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB, "
+            "plain-SC results with pruning mode R0+R1 (proven bit-identical)")
+
+
+def packed_flags(name, n):
+    """Information flags of a packaged frozen set, read without the product package (the reference arm must not load it)."""
+    raw = np.frombuffer(open(os.path.join(ROOT, "sc_polar_decoder_hls_b200", "data", name + ".bits"), "rb").read(), np.uint8)
+    return np.unpackbits(raw, bitorder="little")[:n].copy()
 
 
 # ----------------------------------------------------------------------------- sharding helpers
@@ -124,7 +145,7 @@ def _ref_worker(args):
 
 
 def cpu_decode_rate(flags, llr, kind, cores):
-    """Decode `llr` on the host cores; returns (seconds, kind actually used)."""
+    """Decode `llr` (headline configuration) on the host cores; returns (seconds, kind actually used)."""
     import oracle_lib as ol
     so = os.path.join(ROOT, "oracle", "_ref", "refdec_n4096_p16_q8_ca2_e1.so")
     if kind == "reference" and os.path.exists(so):
@@ -148,11 +169,13 @@ def host_sample(nframes):
 
 
 def run_reference_arm(a):
+    """The reference's CPU implementation only: oracle/ (the checker) and numpy; the product library is not loaded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import sc_polar_decoder_hls_b200 as scpd
-    flags = scpd.packed_flags(CFG["name"], CFG["n"])
+    import oracle_lib as ol
+    ol.build_oracle()
+    flags = packed_flags(CFG["name"], CFG["n"])
     cores = os.cpu_count() or 1
     # probe the rate, then size the per-step sample so the whole run stays within a few minutes
     probe = host_sample(4 * cores)
@@ -168,12 +191,13 @@ def run_reference_arm(a):
         total += cpu_decode_rate(flags, llr, kind, cores)[0]
     ms = 1e3 * total / a.steps
     val = nfr * CFG["k"] / (ms * 1e-3) / 1e9
-    sample = f"{nfr} frames N={CFG['n']} K={CFG['k']} per step, decode only, {cores} host processes"
+    sample = (f"{nfr} frames N={CFG['n']} K={CFG['k']} per step, decode only, {cores} host processes, "
+              "full un-pruned tree (reference FSM, PRUNING_LEVEL 0)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: N=4096 K=3072 plain SC, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB",
-                       "frames_per_step": nfr, "flush": "n/a (host)"},
+            "config": {"workload": WORKLOAD, "frames_per_step": nfr, "flush": "n/a (host)",
+                       "note": "the CPU arm decodes a bounded sample of the same workload and walks the whole tree"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -181,6 +205,78 @@ def run_reference_arm(a):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def int_peak():
+    """Integer-pipe peak of SURVEY 8d's op roofline: lane-instructions per clock and SM, from the committed probe
+    output (tools/probe/lop_probe.cu, asm volatile chains verified in SASS: profiles/int_peak.json)."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "int_peak.json")))
+        return float(j["lop3_lane_instr_per_clk_per_sm"]), j.get("source", "profiles/int_peak.json")
+    except (OSError, ValueError, KeyError):
+        return 64.0, "fallback: 64 lanes/clk/SM (half-rate integer pipe)"
+
+
+def rooflines(n, frames, ms, peaks, sms, sm_mhz):
+    """Both rooflines of SURVEY 8d for `frames` frames decoded in `ms`: bytes N + N/8 at the measured HBM peak, ops
+    I(N) = (N/2) log2 N (7/4 + 1/32) lane-instructions at the measured integer-pipe peak."""
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = frames * (n + n // 8) / (ms * 1e-3) / 1e9
+    lanes, _ = int_peak()
+    alu_peak = sms * lanes * (sm_mhz or 1965.0) * 1e6
+    lane_instr = (n / 2) * np.log2(n) * (7 / 4 + 1 / 32)
+    return {"hbm": {"achieved": ach, "peak": peak, "frac": ach / peak},
+            "alu": {"model_lane_instr_per_frame": lane_instr, "peak_lane_instr_per_s": alu_peak,
+                    "frac": frames * lane_instr / (ms * 1e-3) / alu_peak}}
+
+
+def measure_config(scpd, torch, key, dev, local, steps, warmup, peaks, sms, sm_mhz):
+    """Device-resident throughput of one BASELINE config on this GPU, with its own parity spot check."""
+    import oracle_lib as ol
+    c = CONFIGS[key]
+    n, k, frames = c["n"], c["k"], c["frames"]
+    flags = scpd.packed_flags(c["name"], n)
+    dec = scpd.Decoder(n, k, flags, par=16, llr_bits=8, fmt=scpd.FMT_CA2, extended=1, pruning=scpd.PRUNE_R0_R1, device=local)
+    llr = scpd.channel_generate(n, frames, scpd.sigma(c["ebn0"], k / n), device=local)
+    xhat = torch.empty((frames, n // 32), dtype=torch.int32, device=dev)
+    dec.decode(llr, xhat)
+    torch.cuda.synchronize()
+    chk = c["check"]
+    idx = np.r_[0:chk, frames - chk:frames]
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr[idx].cpu().numpy(), threads=16)
+    ok = bool((xhat[idx].cpu().numpy().view(np.uint32) == want).all())
+    assert ok, f"{key}: CUDA decode differs from the oracle"
+    for _ in range(warmup):
+        dec.decode(llr, xhat)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dec.decode(llr, xhat)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"name": key, "n": n, "k": k, "ebn0_db": c["ebn0"], "batch": frames, "value": frames * k / (ms * 1e-3) / 1e9,
+           "unit": UNIT, "ms": ms, "kernel": dec.last_kernel_name, "parity_frames_checked": int(len(idx)),
+           "roofline": rooflines(n, frames, ms, peaks, sms, sm_mhz)}
+    dec.close()
+    del llr, xhat
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_pipeline(scpd, key, local, nframes):
+    """Information Gb/s of the whole device Monte-Carlo loop (channel + decode + count), host clock around the call."""
+    c = CONFIGS[key]
+    n, k = c["n"], c["k"]
+    dec = scpd.Decoder(n, k, scpd.packed_flags(c["name"], n), device=local)
+    dec.run_ber(c["ebn0"], k / n, nframes)  # allocations (staging buffers of the full batch), jump table
+    t0 = time.perf_counter()
+    cnt = dec.run_ber(c["ebn0"], k / n, nframes)
+    sec = time.perf_counter() - t0
+    dec.close()
+    return {"name": key, "frames": nframes, "value": nframes * k / sec / 1e9, "unit": UNIT, "ms": sec * 1e3,
+            "bit_errors": cnt[0], "frame_errors": cnt[1], "bits": cnt[2]}
+
+
 def run_gpu_arm(a):
     import torch
     import torch.distributed as dist
@@ -244,6 +340,7 @@ def run_gpu_arm(a):
         kms.append(dec.last_kernel_ms())
     dec.kernel_timing(False)
     kernel_ms = float(np.mean(kms))
+    kernel_name = dec.last_kernel_name
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     ms_step = ms_total / a.steps
     value = world * (hi - lo) * k / (ms_step * 1e-3) / 1e9
@@ -268,6 +365,10 @@ def run_gpu_arm(a):
     assert (h_out[:chk].numpy().view(np.uint32) == want).all()
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None  # sampled over the device-resident and the end-to-end regions
+    ops, fg = dec.schedule_stats()
+    dec.close()
+    del llr, xhat, h_llr, h_out
+    torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = {}
@@ -276,48 +377,58 @@ def run_gpu_arm(a):
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = (hi - lo) * (n + n // 8)  # int8 LLR in + packed x^ out per frame
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        nfr = hi - lo
+        alg_bytes = nfr * (n + n // 8)  # int8 LLR in + packed x^ out per frame
         ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        # instruction roofline of SURVEY 8d: I(N) = (N/2) log2 N (7/4 + 1/32) lane-instructions per frame
-        # against the measured 62 lane-instr/clk/SM of the packed-integer / LOP3 pipe (profiles/)
-        lane_instr = (hi - lo) * (n / 2) * np.log2(n) * (7 / 4 + 1 / 32)
-        alu_peak = 148 * 62.0 * 1.965e9
-        alu_frac = lane_instr / (kernel_ms * 1e-3) / alu_peak
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        rf = rooflines(n, nfr, kernel_ms, peaks, sms, sm_mhz)
+        lanes, lanes_src = int_peak()
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of one launch of the dominant kernel at this workload, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+            if tj.get("kernel", "") in kernel_name and tj.get("frames") == nfr:
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except (OSError, ValueError):
             pass
         cores = os.cpu_count() or 1
         nfr_cpu = 64 * cores
-        sec, kind = cpu_decode_rate(flags, llr[:nfr_cpu].cpu().numpy(), "port", cores)
+        llr_cpu = host_sample(nfr_cpu)
+        sec, kind = cpu_decode_rate(flags, llr_cpu, "port", cores)
         cpu_val = nfr_cpu * k / sec / 1e9
-        ops, fg = dec.schedule_stats()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: N=4096 K=3072 plain SC, CA2 Q=8 PAR=16 EXTENDED=1, 3.5 dB",
-                       "kernel": dec.kernel_name, "arithmetic": "bit-sliced: one u32 = one bit plane of an LLR for 32 frames",
-                       "frames_per_step_per_gpu": hi - lo, "frames_per_s": world * (hi - lo) / (ms_step * 1e-3),
+            "config": {"workload": WORKLOAD, "kernel": kernel_name,
+                       "arithmetic": "bit planes over 32 consecutive code positions of one frame per lane (LOP3), fp16x2 "
+                                     "on the FMA pipe inside 32-LLR nodes",
+                       "frames_per_step_per_gpu": nfr, "frames_per_s": world * nfr / (ms_step * 1e-3),
                        "coded_gbps": value * n / k, "schedule_ops": ops, "fg_updates_per_frame": fg,
                        "flush": "inputs (4 GiB of LLRs per GPU) larger than the 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "kernel": "sc_decode_bs_kernel", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "dram": (None if not traffic else
+                                  {"achieved": traffic / (kernel_ms * 1e-3) / 1e9, "frac": traffic / (kernel_ms * 1e-3) / 1e9 / peak,
+                                   "note": "measured DRAM bytes of the launch over its duration: what the kernel really asks of HBM"}),
+                         "kernel": kernel_name.split(" ")[0], "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / ms_step,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "alu": {"model_lane_instr_per_frame": lane_instr / (hi - lo), "peak_lane_instr_per_s": alu_peak,
-                                 "frac": alu_frac},
-                         "note": "algorithmic bytes are N + N/8 per frame; the kernel is bound by the integer/LOP3 pipe, "
-                                 "L1 and the spilled LLR levels together (DESIGN.md section 6)"},
+                         "alu": dict(rf["alu"], peak_lanes_per_clk_per_sm=lanes, peak_source=lanes_src, sm_mhz=sm_mhz),
+                         "note": "algorithmic bytes are N + N/8 per frame; the LLR levels of 256 LLRs and more that do not fit "
+                                 "on chip stream through HBM, which is what bounds the kernel (DESIGN.md section 4)"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": f"{nfr_cpu} frames of the same batch, decode only, {cores} threads"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((hi - lo) * n),
-                    "d2h_bytes_per_step": int((hi - lo) * (n // 32) * 4), "ms_per_step": e2e_ms},
+                             "sample": f"{nfr_cpu} frames of the same workload (host channel chain), decode only, {cores} threads"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(nfr * n),
+                    "d2h_bytes_per_step": int(nfr * (n // 32) * 4), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if world == 1 and not a.no_extras:
+            line["configs"] = [measure_config(scpd, torch, key, dev, local, max(2, min(a.steps, 5)), 3, peaks, sms, sm_mhz)
+                               for key in ("c1", "c2", "c3", "c4", "c5")]
+            line["pipeline"] = [measure_pipeline(scpd, key, local, 1 << 20) for key in ("c1", "c2")]
         emit(line)
     if world > 1:
         dist.barrier()
@@ -351,18 +462,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=CFG["frames"], help="frames per GPU per step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-config table and the pipeline figure")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3
+    if a.impl == "reference":
+        run_reference_arm(a)  # nothing of the product is built or loaded on this arm
+        return
     import __graft_entry__ as ge
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         ge.build()
     else:  # other local ranks wait for rank 0's build instead of racing nvcc
         ge.build_module().wait_for_lib()
-    if a.impl == "reference":
-        run_reference_arm(a)
-    else:
-        run_gpu_arm(a)
+    run_gpu_arm(a)
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscpd.so")
+LIB_PATH = os.environ.get("SCPD_LIB_PATH") or os.path.join(_HERE, "libscpd.so")  # the override is a development aid
 DATA_DIR = os.path.join(_HERE, "data")
 
 FMT_CA2, FMT_SIGMAG = 0, 1

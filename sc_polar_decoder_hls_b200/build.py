@@ -46,6 +46,7 @@ def build_lib(force=False, verbose=False):
             return LIB  # GPU box without a toolkit: use the library that travelled with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt libscpd.so")
     extra = ["-DSCPD_FAST_BUILD"] if os.environ.get("SCPD_FAST_BUILD") else []  # development: fewer instantiations
+    extra += os.environ.get("SCPD_NVCC_EXTRA", "").split()  # development: e.g. -DSCPD_SS_THREADS=768
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

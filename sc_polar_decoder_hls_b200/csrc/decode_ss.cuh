@@ -37,17 +37,20 @@
 #include "ss_plan.h"
 
 #ifndef SS_SIDE_UNROLL
-#define SS_SIDE_UNROLL 2  // 1: the (left, right) loops of the fp16x2 walker stay loops (one copy of the 8-LLR routines)
+#define SS_SIDE_UNROLL 3  // 1: the (left, right) loops of the fp16x2 walker stay loops (one copy of the 8-LLR routines)
 #endif
+// 3: unrolled, with the 16- and 8-LLR routines as out-of-line functions (arguments and results in registers)
 #if SS_SIDE_UNROLL == 1
 #define SS_SIDE_PRAGMA _Pragma("unroll 1")
 #else
 #define SS_SIDE_PRAGMA _Pragma("unroll")
 #endif
 #if defined(__CUDACC__)
+#define SS_NOINLINE __device__ __noinline__
 #define SS_DEV __device__ __forceinline__
 #define SS_ANY(x) __any_sync(0xFFFFFFFFu, (x))
 #else
+#define SS_NOINLINE inline
 #define SS_DEV inline
 #define SS_ANY(x) (x)
 #endif
@@ -63,6 +66,8 @@ struct SsParams {
     unsigned long long nframes, ntasks;
     uint32_t n, log2n, wpf;
     uint32_t lsa, lwin, win_words;
+    uint32_t ltm;          // alpha level kept in tensor memory (0 = none); tm_cols: columns per warp
+    uint32_t tm_cols;
     uint32_t sm_stride, sm_beta_off;  // uint4, per warp
     uint4* ws;
     unsigned long long ws_stride;  // uint4 per warp
@@ -181,6 +186,13 @@ SS_DEV uint32_t h2_pack16(const H2 (&B)[16]) {
     return acc;
 }
 #endif
+
+struct R4 {
+    H2 v[4];
+};
+struct R8 {
+    H2 v[8];
+};
 
 // 8 rows x 32 columns of bits, seen as four 8 x 8 matrices (one per byte column): transpose each of them.
 // in: row p bit (8c + k);  out: row k byte c bit p.  Three delta-swap stages.
@@ -321,7 +333,7 @@ struct Walk {
         node<8, 0, 0>(A, CtDesc8<PAT>(), B);
     }
     // id: index into SS_KNOWN8 (ss_plan.h), anything else: the flags at run time
-    static SS_DEV void dispatch8(uint32_t id, uint32_t fb, uint32_t prune, const H2 (&A)[4], H2 (&B)[4]) {
+    static SS_DEV void dispatch8_body(uint32_t id, uint32_t fb, uint32_t prune, const H2 (&A)[4], H2 (&B)[4]) {
         switch (id) {
             case 1: node8c<0xFFu>(A, B); break;
             case 2: node8c<0xFEu>(A, B); break;
@@ -334,8 +346,24 @@ struct Walk {
             default: node<8, 0, 0>(A, RtDesc8{fb, prune}, B); break;
         }
     }
-    // 16 LLRs (scale 1); ids / fl: pattern ids (4 bits each) and flag bytes of the two 8-LLR children
-    static SS_DEV void walk16(const H2 (&A)[8], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[8]) {
+    // out of line: the routines exist once (instruction cache); four registers in, four out, all in registers
+    static SS_NOINLINE R4 dispatch8_fn(H2 a0, H2 a1, H2 a2, H2 a3, uint32_t id, uint32_t fb, uint32_t prune) {
+        const H2 A[4] = {a0, a1, a2, a3};
+        R4 r;
+        dispatch8_body(id, fb, prune, A, r.v);
+        return r;
+    }
+    static SS_DEV void dispatch8(uint32_t id, uint32_t fb, uint32_t prune, const H2 (&A)[4], H2 (&B)[4]) {
+#if SS_SIDE_UNROLL == 3
+        const R4 r = dispatch8_fn(A[0], A[1], A[2], A[3], id, fb, prune);
+#pragma unroll
+        for (int i = 0; i < 4; i++) B[i] = r.v[i];
+#else
+        dispatch8_body(id, fb, prune, A, B);
+#endif
+    }
+    // 16 LLRs; ids / fl: pattern ids (4 bits each) and flag bytes of the two 8-LLR children
+    static SS_DEV void walk16_body(const H2 (&A)[8], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[8]) {
         H2 BL[4], Bc[4];
 SS_SIDE_PRAGMA
         for (int side = 0; side < 2; side++) {
@@ -370,6 +398,22 @@ SS_SIDE_PRAGMA
             B[i] = h2_mul(BL[i], Bc[i]);
             B[i + 4] = Bc[i];
         }
+    }
+    static SS_NOINLINE R8 walk16_fn(H2 a0, H2 a1, H2 a2, H2 a3, H2 a4, H2 a5, H2 a6, H2 a7, uint32_t ids, uint32_t fl,
+                                    uint32_t prune) {
+        const H2 A[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+        R8 r;
+        walk16_body(A, ids, fl, prune, r.v);
+        return r;
+    }
+    static SS_DEV void walk16(const H2 (&A)[8], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[8]) {
+#if SS_SIDE_UNROLL == 3
+        const R8 r = walk16_fn(A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], ids, fl, prune);
+#pragma unroll
+        for (int i = 0; i < 8; i++) B[i] = r.v[i];
+#else
+        walk16_body(A, ids, fl, prune, B);
+#endif
     }
     // 32 LLRs (scale 1); ids: four pattern ids, fl: the 32 information flags
     static SS_DEV void walk32(const H2 (&A)[16], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[16]) {
@@ -473,7 +517,7 @@ struct SsThread {
 
     SS_DEV SsThread(const SsParams& p_) : p(p_) {}
 
-    SS_DEV uint4* aptr(uint32_t l) const {
+    SS_DEV uint4* aptr(uint32_t l) const {  // not for l == p.ltm (tensor memory)
         if (l == p.log2n) return const_cast<uint4*>(pl);
         return (l <= p.lsa ? sm : wsl) + p.aoff[l];
     }
@@ -500,42 +544,101 @@ struct SsThread {
         q[32] = make_uint4(w[4], w[5], w[6], w[7]);
     }
 
+    // ---------------------------------------------------------------- tensor memory (one alpha level, optional)
+    // The level p.ltm lives in the SM's tensor memory: lane = TMEM lane, the 8 words of chunk c = columns 8c .. 8c+7
+    // of the warp's column range, so one tcgen05.ld / tcgen05.st (32x32b.x8) moves a chunk for the whole warp.
+#if defined(__CUDA_ARCH__)
+    uint32_t tm;  // TMEM address of the warp's column range (lane quarter in bits 31:16)
+    SS_DEV void tm_load(uint32_t c, V& x) const {
+        uint32_t w[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "r"(tm + 8u * c));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        x.s = w[0];
+#pragma unroll
+        for (int k = 0; k < P; k++) x.m[k] = w[1 + k];
+    }
+    SS_DEV void tm_store(uint32_t c, const V& x) const {
+        uint32_t w[8];
+        w[0] = x.s;
+#pragma unroll
+        for (int k = 1; k < 8; k++) w[k] = k <= P ? x.m[k - 1] : 0u;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(tm + 8u * c),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+    }
+    SS_DEV void tm_fence() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+    uint32_t* tm;  // emulation: 8 words per chunk of the lane
+    SS_DEV void tm_load(uint32_t c, V& x) const {
+        x.s = tm[8 * c];
+        for (int k = 0; k < P; k++) x.m[k] = tm[8 * c + 1 + k];
+    }
+    SS_DEV void tm_store(uint32_t c, const V& x) const {
+        tm[8 * c] = x.s;
+        for (int k = 1; k < 8; k++) tm[8 * c + k] = k <= P ? x.m[k - 1] : 0u;
+    }
+    SS_DEV void tm_fence() const {}
+#endif
+
     // ---------------------------------------------------------------- nodes of 128 LLRs and more
-    // alpha[l-1] chunk c = f(alpha[l] chunk c, chunk c + half)                   F_STATE my_module.h:373-445
-    SS_DEV void op_f(uint32_t l) {
-        const uint4* src = aptr(l);
-        uint4* dst = aptr(l - 1);
-        const uint32_t half = 1u << (l - 6);
-        for (uint32_t c = 0; c < half; c += 2) {
-            V a0, b0, a1, b1, r0, r1;
-            load(src + c * 64u, a0);
-            load(src + (c + half) * 64u, b0);
-            load(src + (c + 1u) * 64u, a1);
-            load(src + (c + 1u + half) * 64u, b1);
-            bs::f_op<P>(a0, b0, r0);
-            bs::f_op<P>(a1, b1, r1);
-            store(dst + c * 64u, r0);
-            store(dst + (c + 1u) * 64u, r1);
+    // One pair of input chunks (c, c + half) of alpha[l]
+    template <bool SRC_TM>
+    SS_DEV void load_pair(const uint4* src, uint32_t c, uint32_t half, V& a, V& b) const {
+        if constexpr (SRC_TM) {
+            tm_load(c, a);
+            tm_load(c + half, b);
+        } else {
+            load(src + c * 64u, a);
+            load(src + (c + half) * 64u, b);
         }
     }
-    // alpha[l-1] = g(alpha[l], beta of the left child); zero: left child all-frozen   G_STATE my_module.h:704-781
-    SS_DEV void op_g(uint32_t l, uint32_t wd, bool zero) {
-        const uint4* src = aptr(l);
-        uint4* dst = aptr(l - 1);
+    template <bool DST_TM>
+    SS_DEV void store_chunk(uint4* dst, uint32_t c, const V& r) const {
+        if constexpr (DST_TM)
+            tm_store(c, r);
+        else
+            store(dst + c * 64u, r);
+    }
+    // alpha[l-1] chunk c = f(alpha[l] chunk c, chunk c + half)                   F_STATE my_module.h:373-445
+    // alpha[l-1] chunk c = g(..., beta word c of the left child), beta = 0 when it is all-frozen   G_STATE :704-781
+    // Two chunks per trip, software-pipelined: the loads of the next chunk are in flight while this one is computed
+    // (alpha levels in the workspace / plane buffer answer from L2 or DRAM).
+    template <bool G, bool SRC_TM, bool DST_TM>
+    SS_DEV void op_x(uint32_t l, uint32_t wd, bool zero) {
+        const uint4* src = SRC_TM ? nullptr : aptr(l);
+        uint4* dst = DST_TM ? nullptr : aptr(l - 1);
         const uint32_t half = 1u << (l - 6);
+        const uint32_t* ub = (G && !zero) ? bword(l - 1, wd) : nullptr;  // words wd .. wd + half - 1 lie in one storage
+        V a0, b0, a1, b1, r;
+        load_pair<SRC_TM>(src, 0, half, a0, b0);
         for (uint32_t c = 0; c < half; c += 2) {
-            V a0, b0, a1, b1, r0, r1;
-            load(src + c * 64u, a0);
-            load(src + (c + half) * 64u, b0);
-            load(src + (c + 1u) * 64u, a1);
-            load(src + (c + 1u + half) * 64u, b1);
+            load_pair<SRC_TM>(src, c + 1u, half, a1, b1);
             uint2 u = make_uint2(0u, 0u);
-            if (!zero) u = *reinterpret_cast<const uint2*>(bword(l - 1, wd + c));
-            bs::g_sat_ca2<P>(a0, b0, u.x, r0);
-            bs::g_sat_ca2<P>(a1, b1, u.y, r1);
-            store(dst + c * 64u, r0);
-            store(dst + (c + 1u) * 64u, r1);
+            if (G && !zero) u = *reinterpret_cast<const uint2*>(ub + (c >> 2) * 128u + (c & 3u));
+            if constexpr (G)
+                bs::g_sat_ca2<P>(a0, b0, u.x, r);
+            else
+                bs::f_op<P>(a0, b0, r);
+            store_chunk<DST_TM>(dst, c, r);
+            if (c + 2u < half) load_pair<SRC_TM>(src, c + 2u, half, a0, b0);
+            if constexpr (G)
+                bs::g_sat_ca2<P>(a1, b1, u.y, r);
+            else
+                bs::f_op<P>(a1, b1, r);
+            store_chunk<DST_TM>(dst, c + 1u, r);
         }
+        if constexpr (DST_TM) tm_fence();
+    }
+    template <bool G>
+    SS_DEV void op_fg(uint32_t l, uint32_t wd, bool zero) {
+        if (l == p.ltm)
+            op_x<G, true, false>(l, wd, zero);
+        else if (l == p.ltm + 1u)
+            op_x<G, false, true>(l, wd, zero);
+        else
+            op_x<G, false, false>(l, wd, zero);
     }
     // node (l, wd) := (left ^ right, right); copy: the left child is all-frozen      H_STATE my_module.h:903-932
     SS_DEV void op_h(uint32_t l, uint32_t wd, bool copy) {
@@ -553,18 +656,22 @@ struct SsThread {
             *q = x;
             return;
         }
-        const bool move = (l - 1 < p.lwin) != (l < p.lwin);  // children in the window, the node in the workspace
+        // children in the window and the node in the workspace: the right half moves along
+        const bool move = l == p.lwin;
+        const uint4* cl = bquad(l - 1, wd);
+        const uint4* cr = bquad(l - 1, wd + nw);
+        uint4* d = bquad(l, wd);
         for (uint32_t i = 0; i < nw; i += 4) {
-            uint4 x = *bquad(l - 1, wd + nw + i);
-            if (move) *bquad(l, wd + nw + i) = x;
+            uint4 x = cr[i * 8u];  // quad index advances by 32 per 4 words
+            if (move) d[(nw + i) * 8u] = x;
             if (!copy) {
-                const uint4 y = *bquad(l - 1, wd + i);
+                const uint4 y = cl[i * 8u];
                 x.x ^= y.x;
                 x.y ^= y.y;
                 x.z ^= y.z;
                 x.w ^= y.w;
             }
-            *bquad(l, wd + i) = x;
+            d[i * 8u] = x;
         }
     }
     SS_DEV void op_r0(uint32_t l, uint32_t wd) {
@@ -576,24 +683,30 @@ struct SsThread {
         for (uint32_t i = 0; i < nw; i += 4) *bquad(l, wd + i) = make_uint4(0u, 0u, 0u, 0u);
     }
     // hard decision of alpha[l]; returns true (warp-uniform) when some LLR of some frame is zero
-    SS_DEV bool op_hd(uint32_t l, uint32_t wd) {
-        const uint4* src = aptr(l);
+    template <bool SRC_TM>
+    SS_DEV bool op_hd_x(uint32_t l, uint32_t wd) {
+        const uint4* src = SRC_TM ? nullptr : aptr(l);
         const uint32_t nc = 1u << (l - 5);
+        uint4* d = bquad(l, wd);
         uint32_t z = 0u;
         for (uint32_t c = 0; c < nc; c += 4) {
             uint32_t x[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 V a;
-                load(src + (c + k) * 64u, a);
+                if constexpr (SRC_TM)
+                    tm_load(c + k, a);
+                else
+                    load(src + (c + k) * 64u, a);
                 const uint32_t nz = bs::nonzero<P>(a);
                 z |= ~nz;
                 x[k] = a.s & nz;
             }
-            *bquad(l, wd + c) = make_uint4(x[0], x[1], x[2], x[3]);
+            d[c * 8u] = make_uint4(x[0], x[1], x[2], x[3]);
         }
         return SS_ANY(z != 0u);
     }
+    SS_DEV bool op_hd(uint32_t l, uint32_t wd) { return l == p.ltm ? op_hd_x<true>(l, wd) : op_hd_x<false>(l, wd); }
 
     // ---------------------------------------------------------------- nodes of 64 and 32 LLRs
     // partial-sum word of a node of 32 LLRs given as one chunk of planes (out of line: one copy of the walker)
@@ -677,15 +790,12 @@ struct SsThread {
             switch (code) {
                 case SS_END: return;
                 case SS_F:
-                    op_f(l);
+                    op_fg<false>(l, wd, false);
                     pc++;
                     break;
                 case SS_G:
-                    op_g(l, wd, false);
-                    pc++;
-                    break;
                 case SS_G0:
-                    op_g(l, wd, true);
+                    op_fg<true>(l, wd, code == SS_G0);
                     pc++;
                     break;
                 case SS_H:
@@ -717,8 +827,10 @@ struct SsThread {
     // the root's partial sums are the packed row of the lane's frame (wrapper_out.h:31-33 laid end to end)
     SS_DEV void write_output(unsigned long long frame) {
         if (frame >= p.nframes) return;
-        uint32_t* row = p.xhat + frame * p.wpf;
-        for (uint32_t w = 0; w < p.wpf; w += 4) *reinterpret_cast<uint4*>(row + w) = *bquad(p.log2n, w);
+        uint4* out = reinterpret_cast<uint4*>(p.xhat + frame * p.wpf);
+        const uint4* b = bquad(p.log2n, 0);
+#pragma unroll 1
+        for (uint32_t q = 0; q < p.wpf / 4u; q++) out[q] = b[q * 32u];
     }
 };
 
@@ -772,6 +884,27 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     SsThread<Q, LOG2PAR, EXT> t(p);
     t.sm = ss_smem + (size_t)warp * p.sm_stride + lane;
     uint32_t* sm_sched = reinterpret_cast<uint32_t*>(ss_smem + (size_t)nwarps * p.sm_stride);
+    // tensor memory for the alpha level p.ltm: warp w owns lanes 32 (w % 4) .. +31 (the only ones it can reach) and the
+    // column range (w / 4) * tm_cols .. of the CTA's allocation
+    uint32_t tm_base = 0u, tm_alloc_cols = 0u;
+    if (p.ltm) {
+        tm_alloc_cols = 32u;
+        while (tm_alloc_cols < p.tm_cols * (uint32_t)((nwarps + 3) / 4)) tm_alloc_cols <<= 1;
+        uint32_t* slot = sm_sched + p.sched_words;
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(slot)),
+                         "r"(tm_alloc_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tm_base = *reinterpret_cast<volatile uint32_t*>(slot);
+        t.tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * p.tm_cols;
+        __syncthreads();  // the slot is re-used below
+    }
     if (p.sched_words) {
         for (uint32_t i = threadIdx.x; i < p.sched_words; i += blockDim.x) sm_sched[i] = __ldg(p.sched + i);
         __syncthreads();
@@ -779,12 +912,18 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     } else {
         t.sched = p.sched;
     }
-    const unsigned long long slot = (unsigned long long)blockIdx.x * nwarps + warp;
-    t.wsl = p.ws + slot * p.ws_stride + lane;
-    for (unsigned long long task = slot; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {
+    const unsigned long long slot_id = (unsigned long long)blockIdx.x * nwarps + warp;
+    t.wsl = p.ws + slot_id * p.ws_stride + lane;
+    for (unsigned long long task = slot_id; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {
         t.pl = p.planes + task * p.planes_stride + lane;
         t.run();
         t.write_output(task * 32ull + lane);
+    }
+    if (p.ltm) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(tm_alloc_cols) : "memory");
     }
 }
 #endif

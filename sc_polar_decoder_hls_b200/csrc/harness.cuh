@@ -78,23 +78,27 @@ __device__ __forceinline__ int quantize_llr(float y) {  // sc_quantizer.h:77-80 
     return max(-31, min(31, iv));
 }
 
-// One warp per frame.  Lane l produces draws [l*c, (l+1)*c) of the frame, c = n/64 (n >= 64), so
-// it writes 2c consecutive LLR bytes.  For n < 64 lane 0 produces the whole frame.
+// One warp per BLOCK of F consecutive frames (F = 32768 / n for n < 32768, else 1): the block's F n / 2 draws of each
+// stream are contiguous in the stream and its F n LLR bytes contiguous in memory.  Lane l produces the draws
+// [l c, (l + 1) c) of the block, c = F n / 64 = 2^log2c, i.e. 2c consecutive LLR bytes, 16 at a time.  The jump to the
+// block start and the 31-step chain that hands every lane its own stream position are paid once per block instead of
+// once per frame (at n = 1024 they cost four times the draws themselves).
+// fast != 0: logf / sinf / cosf through the SFU approximations (__logf, __sincosf): the uniform stream is the same,
+// the Gaussian samples differ in the last bits, a quantised LLR differs by one step on about 1e-5 of the samples.
 __global__ void __launch_bounds__(128)
 channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nframes, uint32_t seed, float sigma,
-               const uint8_t* __restrict__ codeword, int per_frame, int8_t* __restrict__ llr, XsJumpTable jt,
-               int log2c /* log2(n/64), or -1 */) {
+               const uint8_t* __restrict__ codeword, int per_frame, int8_t* __restrict__ llr, XsJumpTable jt, int log2c,
+               uint32_t fpb /* frames per block */, int fast) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long f = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (f >= nframes) return;
+    const unsigned long long blk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long f0 = blk * fpb;
+    if (f0 >= nframes) return;
     Xs128 a, b;
     xs128_seed(a, b, seed);
-    const unsigned long long start = (first_frame + f) * (unsigned long long)(n / 2);
+    const unsigned long long start = (first_frame + f0) * (unsigned long long)(n / 2);
     a = xs128_jump(jt, a, start, lane);
     b = xs128_jump(jt, b, start, lane);
-    uint32_t ndraw = n / 2;
-    if (log2c >= 0) {
-        // chain: lane l needs the state advanced by l*c draws; 31 cooperative products by T^c
+    {   // chain: lane l needs the state advanced by l * c draws; 31 cooperative products by T^c
         Xs128 ma = a, mb = b;
         const uint4* tc = jt.cols + (size_t)log2c * 128;
         for (int l = 1; l < 32; l++) {
@@ -107,29 +111,60 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
         }
         a = ma;
         b = mb;
-        ndraw = 1u << log2c;
-    } else if (lane != 0) {
-        return;
     }
-    const uint32_t first_draw = (log2c >= 0) ? (uint32_t)lane * ndraw : 0u;
-    const uint8_t* cw = codeword ? (per_frame ? codeword + f * n : codeword) : nullptr;
-    int8_t* out = llr + f * n;
+    const unsigned long long c = 1ull << log2c;
+    const unsigned long long byte0 = 2ull * c * (unsigned long long)lane;  // first LLR byte of this lane inside the block
+    const unsigned long long valid = (nframes - f0 < fpb ? nframes - f0 : (unsigned long long)fpb) * n;  // bytes of the block
+    int8_t* out = llr + f0 * n;
     const float two_pi = __fmul_rn(2.0f, 3.14159265358979f);  // sc_awgn.h:61-62
-    for (uint32_t d = 0; d < ndraw; d++) {
-        float r1 = xs128_uniform(xs128_next(a));
-        float r2 = xs128_uniform(xs128_next(b));
-        r1 = fmaxf(r1, 5.9604644775390625e-08f);  // the reference has UB at r1 == 0
-        const float y = __fmul_rn(two_pi, r2);             // sc_awgn.h:67
-        const float x = sqrtf(__fmul_rn(-2.0f, logf(r1)));  // :68
-        float sn, cs;
-        sincosf(y, &sn, &cs);
-        const float ph = __fmul_rn(x, sn), qu = __fmul_rn(x, cs);  // :74-77
-        const uint32_t i = 2u * (first_draw + d);
-        const float s0 = (cw && cw[i]) ? -1.0f : 1.0f;  // sc_bpsk.h:53
-        const float s1 = (cw && cw[i + 1]) ? -1.0f : 1.0f;
-        const int q0 = quantize_llr(__fadd_rn(s0, __fmul_rn(ph, sigma)));  // sc_adder.h:139-140
-        const int q1 = quantize_llr(__fadd_rn(s1, __fmul_rn(qu, sigma)));
-        *reinterpret_cast<char2*>(out + i) = make_char2((signed char)q0, (signed char)q1);
+    const uint32_t nmask = n - 1u;
+    const bool aligned = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
+    // 16 bytes (8 draws) per store; a lane's range is a multiple of 16 bytes for every n >= 2 ... when 2c >= 16,
+    // shorter ranges (2c = 2, 4, 8: blocks of fewer than 256 bytes) store byte pairs
+    const uint32_t per = c >= 8 ? 8u : (uint32_t)c;
+    for (unsigned long long d = 0; d < c; d += per) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        const unsigned long long i0 = byte0 + 2ull * d;  // byte offset inside the block
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) {
+            if (k >= per) break;
+            float r1 = xs128_uniform(xs128_next(a));
+            float r2 = xs128_uniform(xs128_next(b));
+            r1 = fmaxf(r1, 5.9604644775390625e-08f);  // the reference has UB at r1 == 0
+            const float y = __fmul_rn(two_pi, r2);  // sc_awgn.h:67
+            float x, sn, cs;
+            if (fast) {
+                x = sqrtf(__fmul_rn(-2.0f, __logf(r1)));
+                __sincosf(y, &sn, &cs);
+            } else {
+                x = sqrtf(__fmul_rn(-2.0f, logf(r1)));  // :68
+                sincosf(y, &sn, &cs);
+            }
+            const float ph = __fmul_rn(x, sn), qu = __fmul_rn(x, cs);  // :74-77
+            float s0 = 1.0f, s1 = 1.0f;  // sc_bpsk.h:53
+            if (codeword) {
+                const unsigned long long i = i0 + 2u * k;
+                const uint8_t* cw = per_frame ? codeword + (f0 + i / n) * n : codeword;
+                const uint32_t pos = (uint32_t)i & nmask;
+                s0 = cw[pos] ? -1.0f : 1.0f;
+                s1 = cw[pos + 1] ? -1.0f : 1.0f;
+            }
+            const int q0 = quantize_llr(__fadd_rn(s0, __fmul_rn(ph, sigma)));  // sc_adder.h:139-140
+            const int q1 = quantize_llr(__fadd_rn(s1, __fmul_rn(qu, sigma)));
+            w[k >> 1] |= (((uint32_t)q0 & 0xFFu) | (((uint32_t)q1 & 0xFFu) << 8)) << (16 * (k & 1));
+        }
+        if (i0 < valid) {
+            if (per == 8u && aligned && i0 + 16u <= valid) {
+                *reinterpret_cast<uint4*>(out + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {  // short lane ranges (n < 16 at the end of the batch) or a buffer that is not 16-byte aligned
+                for (uint32_t k = 0; k < per; k++)
+                    if (i0 + 2u * k < valid) {
+                        const uint32_t h = w[k >> 1] >> (16 * (k & 1));
+                        out[i0 + 2u * k] = (int8_t)(h & 0xFFu);
+                        out[i0 + 2u * k + 1] = (int8_t)((h >> 8) & 0xFFu);
+                    }
+            }
+        }
     }
 }
 

@@ -87,7 +87,11 @@ static int jump_table_device(int device, XsJumpTable* out) {
         const auto& h = jump_table_host();
         uint4* d = nullptr;
         CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(Bits128)));
-        CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(Bits128), cudaMemcpyHostToDevice));
+        const cudaError_t ce = cudaMemcpy(d, h.data(), h.size() * sizeof(Bits128), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail(ce, "jump table upload");
+        }
         it = g_jt_dev.emplace(device, d).first;
     }
     out->cols = it->second;
@@ -149,7 +153,9 @@ struct scpd_decoder {
     size_t bs_planes_bytes = 0;
     // slot-sliced kernel plan (decode_ss.cuh): lane = frame; ss_ok == false: not available for this configuration
     bool ss_ok = false;
-    int ss_warps = 12;
+    int ss_warps = 16;
+    int ss_max_log2n = 14;
+    unsigned long long ss_min_tasks = 0;
     bool ss_sched_smem = false;
     SsPlan ss_plan;
     std::vector<uint32_t> ss_sched_host;
@@ -306,15 +312,21 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
     d->ss_sched_smem = d->ss_sched_host.size() <= (size_t)env_int("SCPD_SS_SCHED_SMEM_WORDS", 2048);
     const size_t total = (size_t)227 * 1024 - (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
     const size_t per_warp = std::min<size_t>(total / d->ss_warps, (size_t)env_int("SCPD_SS_SMEM_KB", 1024) * 1024);
-    if (!ss_make_plan(d->log2n, per_warp, &d->ss_plan, env_int("SCPD_SS_LSA", -1), env_int("SCPD_SS_LWIN", -1))) return SCPD_OK;
-    const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * d->ss_warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
+    // one alpha level in tensor memory: 512 columns shared by the warps that sit on the same 32 TMEM lanes
+    const uint32_t tm_cols = 512u / (uint32_t)((d->ss_warps + 3) / 4);
+    if (!ss_make_plan(d->log2n, per_warp - 16, &d->ss_plan, env_int("SCPD_SS_LSA", -1), env_int("SCPD_SS_LWIN", -1), tm_cols,
+                      env_int("SCPD_SS_LTM", -1)))
+        return SCPD_OK;
+    const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * d->ss_warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     d->ss_ok = true;
+    d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", 14);
+    d->ss_min_tasks = (unsigned long long)env_int("SCPD_SS_MIN_TASKS", 4 * d->num_sms);
     if (env_int("SCPD_VERBOSE", 0))
         fprintf(stderr, "[scpd] slot-sliced kernel: %d warps/CTA, alpha levels 6..%u and partial sums below level %u in smem, "
-                "%u B/warp, workspace %llu B/warp, %zu schedule words (%s)\n", d->ss_warps, d->ss_plan.lsa, d->ss_plan.lwin,
-                d->ss_plan.sm_stride * 16u, d->ss_plan.ws_stride * 16ull, d->ss_sched_host.size(),
-                d->ss_sched_smem ? "shared" : "global");
+                "%u B/warp, alpha level %u in tensor memory (%u columns/warp), workspace %llu B/warp, %zu schedule words (%s)\n",
+                d->ss_warps, d->ss_plan.lsa, d->ss_plan.lwin, d->ss_plan.sm_stride * 16u, d->ss_plan.ltm, d->ss_plan.tm_cols,
+                d->ss_plan.ws_stride * 16ull, d->ss_sched_host.size(), d->ss_sched_smem ? "shared" : "global");
     return SCPD_OK;
 }
 
@@ -645,6 +657,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
 extern "C" void scpd_destroy(scpd_decoder* d) {
     if (!d) return;
     cudaSetDevice(d->device);
+    cudaDeviceSynchronize();  // stream-ordered scratch (grow) is released with plain cudaFree below
     cudaFree(d->d_sched);
     cudaFree(d->d_ws);
     cudaFree(d->fast.d_sched);
@@ -676,6 +689,19 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     delete d;
 }
 
+// Handle-owned scratch grows in stream order (cudaFreeAsync / cudaMallocAsync on the caller's stream): scpd_decode
+// stays asynchronous even when a larger batch than any before arrives.  Work queued earlier on the same stream keeps
+// the old buffer until it has run; a handle is used from one stream at a time (scpd.h).
+static int grow(void** ptr, size_t* have, size_t need, cudaStream_t st) {
+    if (need <= *have) return SCPD_OK;
+    if (*ptr) CUDA_TRY(cudaFreeAsync(*ptr, st));
+    *ptr = nullptr;
+    *have = 0;
+    CUDA_TRY(cudaMallocAsync(ptr, need, st));
+    *have = need;
+    return SCPD_OK;
+}
+
 static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
     const unsigned long long num_fp = (nframes + 1) / 2;
     const FastPlan& fp = pick_fast(d, num_fp);
@@ -685,13 +711,9 @@ static int decode_fast(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uin
     const unsigned long long max_grid = (unsigned long long)d->num_sms * fp.ctas_per_sm;
     if (grid > max_grid) grid = max_grid;
     const size_t ws_need = (size_t)(grid * fp_per_cta * fp.ws_stride);
-    if (ws_need > d->fast_ws_bytes) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d->d_fast_ws);
-        d->d_fast_ws = nullptr;
-        d->fast_ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&d->d_fast_ws, ws_need));
-        d->fast_ws_bytes = ws_need;
+    {
+        const int grc = grow((void**)&d->d_fast_ws, &d->fast_ws_bytes, ws_need, st);
+        if (grc) return grc;
     }
     FastParams p;
     p.sched = fp.d_sched;
@@ -730,23 +752,15 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     const unsigned long long max_grid = (unsigned long long)d->num_sms * d->bs_ctas_per_sm;
     if (grid > max_grid) grid = max_grid;
     const size_t ws_need = (size_t)(grid * gpc * d->bs_plan.ws_stride);
-    if (ws_need > d->bs_ws_bytes) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d->d_bs_ws);
-        d->d_bs_ws = nullptr;
-        d->bs_ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&d->d_bs_ws, ws_need));
-        d->bs_ws_bytes = ws_need;
+    {
+        const int grc = grow((void**)&d->d_bs_ws, &d->bs_ws_bytes, ws_need, st);
+        if (grc) return grc;
     }
     const size_t pl_stride = bs_planes_bytes((int)d->cfg.llr_bits, d->log2n);
     const size_t pl_need = (size_t)ngroups * pl_stride;
-    if (pl_need > d->bs_planes_bytes) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d->d_bs_planes);
-        d->d_bs_planes = nullptr;
-        d->bs_planes_bytes = 0;
-        CUDA_TRY(cudaMalloc(&d->d_bs_planes, pl_need));
-        d->bs_planes_bytes = pl_need;
+    {
+        const int grc = grow((void**)&d->d_bs_planes, &d->bs_planes_bytes, pl_need, st);
+        if (grc) return grc;
     }
     {   // int8 rows -> bit planes, one warp per (group, 128 LLRs)
         const unsigned long long tasks = ngroups * (d->cfg.n / 128u);
@@ -790,17 +804,6 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     return SCPD_OK;
 }
 
-static int grow(void** ptr, size_t* have, size_t need, cudaStream_t st) {
-    if (need <= *have) return SCPD_OK;
-    CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(*ptr);
-    *ptr = nullptr;
-    *have = 0;
-    CUDA_TRY(cudaMalloc(ptr, need));
-    *have = need;
-    return SCPD_OK;
-}
-
 // slot-sliced kernel: lane = frame, 32 frames per warp ("task")
 static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint32_t* d_xhat, cudaStream_t st) {
     const unsigned long long ntasks = (nframes + 31) / 32;
@@ -838,13 +841,15 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.lsa = d->ss_plan.lsa;
     p.lwin = d->ss_plan.lwin;
     p.win_words = d->ss_plan.win_words;
+    p.ltm = d->ss_plan.ltm;
+    p.tm_cols = d->ss_plan.tm_cols;
     p.sm_stride = d->ss_plan.sm_stride;
     p.sm_beta_off = d->ss_plan.sm_beta_off;
     p.ws = d->d_ss_ws;
     p.ws_stride = d->ss_plan.ws_stride;
     p.ws_beta_off = d->ss_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->ss_plan.aoff[l];
-    const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
+    const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(warps * 32)), smem, st>>>(p);
@@ -861,13 +866,9 @@ static int decode_raw(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint
     const unsigned long long max_grid = (unsigned long long)d->num_sms * d->raw_ctas_per_sm;
     if (grid > max_grid) grid = max_grid;
     const size_t ws_need = (size_t)(grid * f_per_cta * d->raw_ws_words * 4ull);
-    if (ws_need > d->raw_ws_bytes) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d->d_raw_ws);
-        d->d_raw_ws = nullptr;
-        d->raw_ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&d->d_raw_ws, ws_need));
-        d->raw_ws_bytes = ws_need;
+    {
+        const int grc = grow((void**)&d->d_raw_ws, &d->raw_ws_bytes, ws_need, st);
+        if (grc) return grc;
     }
     RawParams p;
     p.sched = d->d_raw_sched;
@@ -904,9 +905,11 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (d->raw_only) return decode_raw(d, d_llr, nframes, d_xhat, st);
-    // The slot-sliced kernel (a lane per frame) is the default for CA2 once the batch gives every SM a few warps
+    // The slot-sliced kernel (a lane per frame) is the default for CA2 up to N = 2^14 once the batch gives every SM
+    // a few warps (measured, profiles/tuning_r2.md: 347 / 384 Gb/s against 231 / 288 at N = 1024 / 4096; from N = 2^15
+    // its 32-frame workspace per warp costs more DRAM traffic than the frame-sliced kernel's, which wins there)
     if (d->ss_ok && (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0 &&
-        (nframes + 31) / 32 >= (unsigned long long)env_int("SCPD_SS_MIN_TASKS", d->kernel_pinned ? 1 : 2 * d->num_sms))
+        (d->kernel_pinned || (d->log2n <= d->ss_max_log2n && (nframes + 31) / 32 >= d->ss_min_tasks)))
         return decode_ss(d, d_llr, nframes, d_xhat, st);
     // One warp walks the tree of a 32-frame group alone, so the bit-sliced kernel needs many groups to fill the
     // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 24 k at N = 4096,
@@ -927,13 +930,9 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     const unsigned long long max_grid = (unsigned long long)d->num_sms * d->ctas_per_sm;
     if (grid > max_grid) grid = max_grid;
     const size_t ws_need = (size_t)(grid * fp_per_cta * d->ws_words_per_fp * 4ull);
-    if (ws_need > d->ws_bytes) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d->d_ws);
-        d->d_ws = nullptr;
-        d->ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&d->d_ws, ws_need));
-        d->ws_bytes = ws_need;
+    {
+        const int grc = grow((void**)&d->d_ws, &d->ws_bytes, ws_need, st);
+        if (grc) return grc;
     }
     DecodeParams p;
     p.sched = d->d_sched;
@@ -1031,7 +1030,12 @@ extern "C" int scpd_decode_host(scpd_decoder* d, const int8_t* h_llr, size_t nfr
         CUDA_TRY(cudaStreamWaitEvent(d->st_comp, d->ev_in[b], 0));
         if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(d->st_comp, d->ev_out[b], 0));  // copy-out i-2 has drained this buffer
         rc = scpd_decode(d, d->d_llr2[b], nb, d->d_xhat2[b], d->st_comp);
-        if (rc) return rc;
+        if (rc) {  // nothing may still be writing into the caller's buffers when the error is returned
+            cudaStreamSynchronize(d->st_in);
+            cudaStreamSynchronize(d->st_comp);
+            cudaStreamSynchronize(d->st_out);
+            return rc;
+        }
         CUDA_TRY(cudaEventRecord(d->ev_dec[b], d->st_comp));
         CUDA_TRY(cudaStreamWaitEvent(d->st_out, d->ev_dec[b], 0));
         CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h_xhat) + f0 * row_out, d->d_xhat2[b], nb * row_out,
@@ -1067,7 +1071,7 @@ extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
     if (!d) return "";
     if (d->raw_only)
         snprintf(buf, sizeof buf, "sc_decode_raw_kernel (raw W-bit patterns, %d lanes per frame)", d->raw_group);
-    else if (d->ss_ok)
+    else if (d->ss_ok && (d->log2n <= d->ss_max_log2n || !d->bs_ok))
         snprintf(buf, sizeof buf, "sc_decode_ss_kernel (slot-sliced, lane per frame, %d warps/CTA)", d->ss_warps);
     else if (d->bs_ok)
         snprintf(buf, sizeof buf, "sc_decode_bs_kernel (bit-sliced, %d lanes per 32-frame group, %d warps/CTA)", d->bs_group,
@@ -1101,6 +1105,11 @@ extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
 }
 extern "C" int scpd_schedule_stats(const scpd_decoder* d, uint64_t* n_ops, uint64_t* n_fg) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_schedule_stats: null decoder");
+    if (!d->raw_only && d->ss_ok && d->log2n <= d->ss_max_log2n) {
+        if (n_ops) *n_ops = d->ss_stats.n_ops;
+        if (n_fg) *n_fg = d->ss_stats.n_f + d->ss_stats.n_g;
+        return SCPD_OK;
+    }
     const ScheduleStats& st = d->raw_only ? d->raw_stats : d->bs_ok ? d->bs_stats : d->fast.group ? d->fast.stats : d->stats;
     if (n_ops) *n_ops = st.n_ops;
     if (n_fg) *n_fg = st.n_f + st.n_g;
@@ -1122,10 +1131,14 @@ extern "C" int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nf
     XsJumpTable jt;
     int rc = jump_table_device(device, &jt);
     if (rc) return rc;
-    const int log2c = n >= 64 ? ilog2(n / 64) : -1;
-    const unsigned grid = (unsigned)((nframes + 3) / 4);
+    // a warp per block of frames: 32768 LLRs when the frame is shorter than that (harness.cuh)
+    const uint32_t fpb = n < 32768u ? 32768u / n : 1u;
+    const int log2c = ilog2(fpb * n / 64u);
+    const unsigned long long nblk = (nframes + fpb - 1) / fpb;
+    const unsigned grid = (unsigned)((nblk + 3) / 4);
+    static const int fast_math = env_int("SCPD_CHANNEL_FAST", 0);
     channel_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, d_codeword, per_frame,
-                                                           d_llr, jt, log2c);
+                                                           d_llr, jt, log2c, fpb, fast_math);
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
 }
@@ -1137,54 +1150,75 @@ extern "C" int scpd_count_errors(uint32_t n, size_t nframes, const uint32_t* d_x
     if (!is_pow2(n) || n < 2) return set_error(SCPD_E_CONFIG, "n must be a power of two >= 2");
     const uint32_t wpf = n >= 32 ? n / 32 : 1;
     unsigned long long blocks = (nframes + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int device = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (blocks > (unsigned long long)sms * 8) blocks = (unsigned long long)sms * 8;
     count_errors_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         wpf, n, nframes, d_xhat, d_ref, per_frame, (unsigned long long*)d_counters);
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
 }
 
+// Monte-Carlo loop on the device: generate -> decode -> count, batch after batch.  Generation of batch i + 1 runs on a
+// second stream while batch i is decoded and counted (double-buffered LLR / x^ staging), so the SFU-bound channel
+// kernel overlaps the LOP3-bound decode.
 extern "C" int scpd_run_ber(scpd_decoder* d, float ebn0_db, float rate, uint64_t first_frame, uint64_t nframes,
                             uint8_t seed, const uint8_t* h_codeword, uint64_t h_counters[6]) {
     if (!d || !h_counters) return set_error(SCPD_E_ARG, "scpd_run_ber: null argument");
     CUDA_TRY(cudaSetDevice(d->device));
     const uint32_t n = d->cfg.n;
-    // batch so that LLR staging stays around 1 GiB, but never fewer than 4 frame groups per SM (large trees)
-    size_t batch = (size_t)((1ull << 30) / n);
-    batch = std::max<size_t>(batch, (size_t)4 * 32 * (size_t)d->num_sms);
-    if (batch < 2) batch = 2;
+    // batch so that LLR staging stays around 0.5 GiB per buffer, but never fewer than 8 tasks of 32 frames per SM
+    size_t batch = (size_t)((1ull << 29) / n);
+    batch = std::max<size_t>(batch, (size_t)8 * 32 * (size_t)d->num_sms);
+    batch &= ~(size_t)31;
     if (batch > nframes) batch = (size_t)nframes;
     if (batch == 0) {
         std::memset(h_counters, 0, 6 * sizeof(uint64_t));
         return SCPD_OK;
     }
-    int rc = ensure_stage(d, batch);
+    int rc = ensure_pipeline(d, batch);
     if (rc) return rc;
-    uint8_t* d_cw = nullptr;
-    uint32_t* d_ref = nullptr;
+    struct Tmp {  // freed on every exit
+        uint8_t* cw = nullptr;
+        uint32_t* ref = nullptr;
+        ~Tmp() {
+            cudaFree(cw);
+            cudaFree(ref);
+        }
+    } tmp;
     if (h_codeword) {
         std::vector<uint32_t> ref(d->wpf, 0);
         for (uint32_t i = 0; i < n; i++)
             if (h_codeword[i] & 1) ref[i >> 5] |= 1u << (i & 31);
-        CUDA_TRY(cudaMalloc(&d_cw, n));
-        CUDA_TRY(cudaMalloc(&d_ref, d->wpf * 4));
-        CUDA_TRY(cudaMemcpy(d_cw, h_codeword, n, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(d_ref, ref.data(), d->wpf * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&tmp.cw, n));
+        CUDA_TRY(cudaMalloc(&tmp.ref, d->wpf * 4));
+        CUDA_TRY(cudaMemcpy(tmp.cw, h_codeword, n, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(tmp.ref, ref.data(), d->wpf * 4, cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMemsetAsync(d->d_counters, 0, 6 * sizeof(unsigned long long), 0));
+    cudaStream_t sg = d->st_in, sd = d->st_comp;  // generator stream, decode + count stream
+    CUDA_TRY(cudaMemsetAsync(d->d_counters, 0, 6 * sizeof(unsigned long long), sd));
     const float sigma = scpd_sigma(ebn0_db, rate);
-    for (uint64_t done = 0; done < nframes && rc == SCPD_OK; done += batch) {
+    size_t i = 0;
+    for (uint64_t done = 0; done < nframes && rc == SCPD_OK; done += batch, i++) {
+        const int b = (int)(i & 1);
         const size_t nb = (size_t)((nframes - done < batch) ? nframes - done : batch);
-        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, d_cw, 0, d->d_llr, 0);
-        if (rc == SCPD_OK) rc = scpd_decode(d, d->d_llr, nb, d->d_xhat, 0);
-        if (rc == SCPD_OK) rc = scpd_count_errors(n, nb, d->d_xhat, d_ref, 0, (uint64_t*)d->d_counters, 0);
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(sg, d->ev_dec[b], 0));  // decode i - 2 has consumed this LLR buffer
+        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, tmp.cw, 0, d->d_llr2[b], sg);
+        if (rc) break;
+        CUDA_TRY(cudaEventRecord(d->ev_in[b], sg));
+        CUDA_TRY(cudaStreamWaitEvent(sd, d->ev_in[b], 0));
+        rc = scpd_decode(d, d->d_llr2[b], nb, d->d_xhat2[b], sd);
+        if (rc) break;
+        CUDA_TRY(cudaEventRecord(d->ev_dec[b], sd));
+        rc = scpd_count_errors(n, nb, d->d_xhat2[b], tmp.ref, 0, (uint64_t*)d->d_counters, sd);
         d->launches += 2;
     }
-    cudaError_t e = cudaMemcpy(h_counters, d->d_counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost);
-    cudaFree(d_cw);
-    cudaFree(d_ref);
+    cudaError_t e1 = cudaStreamSynchronize(sg), e2 = cudaStreamSynchronize(sd);  // also on the error paths: nothing in flight
     if (rc) return rc;
-    if (e != cudaSuccess) return cuda_fail(e, "counter readback");
+    if (e1 != cudaSuccess) return cuda_fail(e1, "generator stream");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "decode stream");
+    CUDA_TRY(cudaMemcpy(h_counters, d->d_counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return SCPD_OK;
 }
 

@@ -17,9 +17,6 @@
 //                           information flags; word 3 = pattern ids of the eight 8-LLR nodes, 4 bits each
 //   SS_XS + 4 words         SS_F / SS_G / SS_G0 at level 7 fused with the SS_SUB of the child it feeds: alpha[6]
 //                           stays in registers for the child's f (it is still stored for the child's g)
-//   SS_FUSE                 X(l) Y(l-1) [Y(l-2)]: an f / g / g0 whose output node starts with f or g0 again;
-//                           the intermediate LLRs stay in registers.  Bits [5:0] = SS_FUSE, the kinds follow in
-//                           a second word (see ss_fuse_word)
 // Node types: 0 mixed, 1 all-frozen, 2 all-information; for nodes of 2 LLRs the code is the flag pair itself:
 // 0 = (0,1), 1 = (0,0), 2 = (1,1), 3 = (1,0).
 #pragma once
@@ -41,7 +38,6 @@ enum : uint32_t {
     SS_R1 = 7,
     SS_SUB = 8,
     SS_XS = 9,      // level-7 op (kind in bits [31:30] of the first descriptor word's upper bits, see below) + SUB
-    SS_FUSE = 10,
 };
 enum : uint32_t { SS_T_MIX = 0, SS_T_R0 = 1, SS_T_R1 = 2 };
 // information-flag patterns of 8-LLR nodes with a specialised routine (bit i = flag of position i); index = pattern
@@ -58,7 +54,7 @@ SS_HD static inline uint32_t ss_op_make(uint32_t code, uint32_t level, uint32_t 
 }
 SS_HD static inline uint32_t ss_op_code(uint32_t w) { return w & 63u; }
 SS_HD static inline uint32_t ss_op_level(uint32_t w) { return (w >> 6) & 31u; }
-SS_HD static inline uint32_t ss_op_word(uint32_t w) { return w >> 11; }  // node offset / 32 = first partial-sum word
+SS_HD static inline uint32_t ss_op_word(uint32_t w) { return (w >> 11) & 0xFFFFFu; }  // node offset / 32 = first partial-sum word
 
 struct SsStats {
     uint64_t n_ops = 0, n_f = 0, n_g = 0, n_r0 = 0, n_r1 = 0, n_sub = 0, n_sub32_mixed = 0;
@@ -246,6 +242,8 @@ static inline std::vector<uint32_t> ss_build_schedule(int log2n, int pruning, co
 struct SsPlan {
     uint32_t lsa = 0;    // alpha levels 6 .. lsa in shared memory, lsa+1 .. log2n-1 in the workspace
     uint32_t lwin = 0;   // partial sums of nodes below level lwin in the shared window (2^lwin code positions)
+    uint32_t ltm = 0;    // this alpha level (above lsa) lives in tensor memory instead; 0 = none
+    uint32_t tm_cols = 0;  // tensor-memory columns per warp (8 per chunk: 2^(ltm - 2))
     uint32_t aoff[24] = {0};
     uint32_t sm_beta_off = 0, sm_stride = 0;  // per warp
     uint32_t ws_beta_off = 0;
@@ -255,7 +253,10 @@ struct SsPlan {
 static inline size_t ss_planes_quads(int log2n) { return (size_t)64u << (log2n - 5); }  // uint4 per 32-frame task
 
 // smem_per_warp in bytes.  Returns false when even the minimum (alpha[6] + a 256-position window) does not fit.
-static inline bool ss_make_plan(int log2n, size_t smem_per_warp, SsPlan* out, int force_lsa = -1, int force_lwin = -1) {
+// tm_cols_avail: tensor-memory columns a warp may use (512 / ceil(warps per CTA / 4)), 0 = do not use tensor memory;
+// want_ltm: -1 = the largest level above lsa that fits, 0 = none, else that level.
+static inline bool ss_make_plan(int log2n, size_t smem_per_warp, SsPlan* out, int force_lsa = -1, int force_lwin = -1,
+                                uint32_t tm_cols_avail = 0, int want_ltm = 0) {
     SsPlan p;
     auto a_quads = [](int l) { return (size_t)64u << (l - 5); };
     auto win_quads = [&](int lwin) { return (size_t)32u * std::max<size_t>(1, (std::min<size_t>((size_t)1 << lwin, (size_t)1 << log2n) / 32 + 3) / 4); };
@@ -286,8 +287,15 @@ static inline bool ss_make_plan(int log2n, size_t smem_per_warp, SsPlan* out, in
     off += win_quads(lwin);
     p.sm_stride = (uint32_t)off;
     p.win_words = (uint32_t)(std::min<size_t>((size_t)1 << lwin, (size_t)1 << log2n) / 32);
+    int ltm = want_ltm;
+    if (want_ltm < 0)  // the largest level that fits: every level costs the same traffic per LLR, the largest holds the most
+        for (ltm = log2n - 1; ltm > lsa && ((uint32_t)1 << (ltm - 2)) > tm_cols_avail;) ltm--;
+    if (ltm <= lsa || ltm < 8 || ltm > log2n - 1 || ((uint32_t)1 << (ltm - 2)) > tm_cols_avail) ltm = 0;
+    p.ltm = (uint32_t)ltm;
+    p.tm_cols = ltm ? (uint32_t)1 << (ltm - 2) : 0u;
     size_t woff = 0;
     for (int l = lsa + 1; l <= log2n - 1; l++) {
+        if (l == ltm) continue;
         p.aoff[l] = (uint32_t)woff;
         woff += a_quads(l);
     }

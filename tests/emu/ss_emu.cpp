@@ -25,7 +25,7 @@ using namespace scpd;
 
 template <int Q, int LOG2PAR, bool EXT>
 static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, size_t nframes, uint32_t* xhat,
-               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats) {
+               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats, int ltm) {
     constexpr int P = Q - 1;
     const uint32_t n = 1u << log2n;
     SsStats st;
@@ -37,7 +37,8 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
         stats[3] = st.n_sub32_mixed;
     }
     SsPlan plan;
-    if (!ss_make_plan(log2n, smem_per_warp, &plan, force_lsa, force_lwin)) return 1;
+    if (!ss_make_plan(log2n, smem_per_warp, &plan, force_lsa, force_lwin, ltm ? 512u : 0u, ltm)) return 1;
+    if (ltm > 0 && plan.ltm != (uint32_t)ltm) return 3;
     const size_t ntasks = (nframes + 31) / 32;
     const size_t pl_stride = ss_planes_quads(log2n);
     std::vector<uint4> planes(ntasks * pl_stride, uint4{0, 0, 0, 0});
@@ -70,6 +71,8 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     p.wpf = n / 32;
     p.lsa = plan.lsa;
     p.lwin = plan.lwin;
+    p.ltm = plan.ltm;
+    p.tm_cols = plan.tm_cols;
     p.win_words = plan.win_words;
     p.sm_stride = plan.sm_stride;
     p.sm_beta_off = plan.sm_beta_off;
@@ -79,12 +82,14 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     std::vector<uint4> smem(plan.sm_stride, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     std::vector<uint4> ws(plan.ws_stride ? plan.ws_stride : 1, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     p.ws = ws.data();
+    std::vector<uint32_t> tmem((size_t)32 * 512, 0xDEADBEEFu);  // 512 columns per lane
     for (size_t task = 0; task < ntasks; task++) {
         for (int lane = 0; lane < 32; lane++) {
             SsThread<Q, LOG2PAR, EXT> t(p);
             t.sm = smem.data() + lane;
             t.wsl = ws.data() + lane;
             t.sched = sched.data();
+            t.tm = tmem.data() + (size_t)lane * 512;
             t.pl = planes.data() + task * pl_stride + lane;
             t.run();
             t.write_output(task * 32ull + lane);
@@ -95,10 +100,10 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
 
 extern "C" int ss_emu_decode(int log2n, int q, int log2par, int ext, int pruning, const uint8_t* flags, const int8_t* llr,
                              size_t nframes, uint32_t* xhat, size_t smem_per_warp, int force_lsa, int force_lwin, int fuse,
-                             uint64_t* stats) {
+                             uint64_t* stats, int ltm) {
 #define SS_CASE(Q, LP, E)                          \
     if (q == Q && log2par == LP && ext == (E ? 1 : 0)) \
-        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats);
+        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats, ltm);
     SS_CASE(8, 4, true)
     SS_CASE(8, 4, false)
     SS_CASE(6, 4, true)

@@ -64,15 +64,32 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
     dec.close()
 
 
-@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "coop4", "coop8", "bs8", "bs16", "bs32", "bs32ws"])
+@pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "coop4", "coop8", "bs8", "bs16", "bs32", "bs32ws",
+                        "ss", "ss12", "ss_notm", "ss_tm8", "ss_nofuse"])
 def kernel_mode(request, monkeypatch):
     """Selects the decode kernel through the library's environment switches (read in scpd_create):
     the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
     workspace early, one warp per CTA), the int16x2 kernel with 2 / 8 / 16 lanes per frame pair, the
     generic kernel, the raw-pattern kernel, and the library's own choice."""
     mode = request.param
-    for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_COOP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS"):
+    for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_COOP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS", "SCPD_SS_WARPS",
+              "SCPD_SS_LTM", "SCPD_SS_LSA", "SCPD_SS_LWIN", "SCPD_SS_FUSE"):
         monkeypatch.delenv(v, raising=False)
+    if mode.startswith("ss"):
+        # the slot-sliced kernel (a lane per frame): default plan (16 warps per CTA, one LLR level in tensor memory),
+        # 12 warps (other tensor-memory column split), no tensor memory, level 8 in tensor memory with a small
+        # partial-sum window, no fused level-7 op
+        monkeypatch.setenv("SCPD_KERNEL", "ss")
+        if mode == "ss12":
+            monkeypatch.setenv("SCPD_SS_WARPS", "12")
+        elif mode == "ss_notm":
+            monkeypatch.setenv("SCPD_SS_LTM", "0")
+        elif mode == "ss_tm8":
+            monkeypatch.setenv("SCPD_SS_LTM", "8")
+            monkeypatch.setenv("SCPD_SS_LWIN", "8")
+        elif mode == "ss_nofuse":
+            monkeypatch.setenv("SCPD_SS_FUSE", "0")
+        return mode
     if mode in ("generic", "raw"):
         monkeypatch.setenv("SCPD_KERNEL", mode)
     elif mode.startswith("coop"):
@@ -93,7 +110,7 @@ def kernel_mode(request, monkeypatch):
 @pytest.mark.parametrize("key,nfr", [("c1", 600), ("c2", 150), ("c3", 8)])
 @pytest.mark.parametrize("prune", [0, 1, 2])
 def test_every_kernel_variant(scpd, kernel_mode, key, nfr, prune):
-    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8", "coop4"):
+    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8", "coop4", "ss", "ss_tm8"):
         pytest.skip("the large tree is covered by one variant per kernel family")
     name, n, k, snr = CONFIG_SETS[key]
     llr = _llrs(21, n, nfr, k, snr).copy()
@@ -236,6 +253,23 @@ def test_baseline_configs(scpd, key, nfr, prune):
     _check(scpd, name, n, k, 16, 8, 1, prune, llr)
 
 
+@pytest.mark.parametrize("key,nfr", [("c2", 100000), ("c3", 4096), ("c4", 512), ("c5", 128)])
+def test_baseline_configs_parity_gate(scpd, key, nfr):
+    """the parity gate before any timing counts -- >= 10^5 channel frames at c2 (c1 has its own
+    test), 4096 / 512 / 128 at c3 / c4 / c5 (the oracle needs seconds per frame of N = 2^19), device-generated LLRs at the
+    configuration's Eb/N0, default kernel choice at that batch size, every frame compared."""
+    import torch
+    name, n, k, snr = CONFIG_SETS[key]
+    flags = scpd.packed_flags(name, n)
+    llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n))
+    dec = scpd.Decoder(n, k, flags)
+    got = dec.decode(llr).cpu().numpy().view(np.uint32)
+    torch.cuda.synchronize()
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr.cpu().numpy(), threads=16)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (key, dec.last_kernel_name, bad[:5])
+
+
 def test_zero_llr_fallback(scpd):
     """All-zero and sparse LLR frames force the rate-1 plain-SC fallback on every node (G3/G10)."""
     name, n, k, _ = CONFIG_SETS["c1"]
@@ -280,6 +314,64 @@ def test_bit_sliced_kernel_edge_cases(scpd, monkeypatch, group):
             llr[-1][::3] = 0
             assert (dec.decode_host(llr) == ol.decode_packed(n, 16, q, fmt, 1, flags, llr)).all(), (fmt, nfr)
         dec.close()
+
+
+def test_slot_sliced_kernel_edge_cases(scpd, monkeypatch):
+    """The slot-sliced kernel pinned (small batches would otherwise go to the int16x2 kernel): arbitrary (non-polar)
+    flag tables -- the run-time fallback of the fp16x2 walker --, zero-heavy and full-range LLRs (the CA2 rate-1
+    fallback on almost every node), ragged last tasks, one-frame batches, the (LLR_BITS, PAR, EXTENDED) variants."""
+    monkeypatch.setenv("SCPD_KERNEL", "ss")
+    rng = np.random.default_rng(2)
+    for n in (128, 256, 1024):
+        for trial in range(3):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-127, 128, size=(77, n)).astype(np.int8)
+            llr[rng.random(llr.shape) < 0.3] = 0
+            llr[0] = 0
+            llr[1] = 127
+            llr[2] = -127
+            for prune in (0, 1, 2):
+                dec = scpd.Decoder(n, int(flags.sum()), flags, par=16, pruning=prune)
+                assert "slot-sliced" in dec.kernel_name
+                assert (dec.decode_host(llr) == ol.decode_packed(n, 16, 8, 0, 1, flags, llr)).all(), (n, trial, prune)
+                dec.close()
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags)
+    for nfr in (1, 2, 31, 32, 33, 65, 257, 1000):
+        llr = ol.test_llrs(rng, n, nfr, k, snr)
+        llr[-1][::3] = 0
+        assert (dec.decode_host(llr) == ol.decode_packed(n, 16, 8, 0, 1, flags, llr)).all(), nfr
+    assert "slot-sliced" in dec.last_kernel_name
+    dec.close()
+    for par, q, ext in ((16, 8, 0), (16, 7, 1), (16, 6, 1), (16, 6, 0), (4, 8, 1), (8, 8, 1), (32, 7, 1), (32, 6, 1)):
+        ma = (1 << (q - 1)) - 1
+        llr = ol.test_llrs(rng, n, 300, k, snr, maxabs=min(31, ma))
+        llr[150:] = rng.integers(-ma, ma + 1, size=(150, n))
+        llr[-1] = 0
+        for prune in (0, 2):
+            dec = scpd.Decoder(n, k, flags, par=par, llr_bits=q, extended=ext, pruning=prune)
+            assert "slot-sliced" in dec.kernel_name, (par, q, ext)
+            assert (dec.decode_host(llr) == ol.decode_packed(n, par, q, 0, ext, flags, llr, threads=8)).all(), (par, q, ext, prune)
+            dec.close()
+
+
+def test_slot_sliced_is_the_default_for_large_batches(scpd):
+    """scpd_decode's kernel choice for CA2 up to N = 2^14: the slot-sliced kernel once the batch gives every SM a few
+    warps, the int16x2 kernel below -- and the same bits whichever kernel runs."""
+    import torch
+    name, n, k, snr = CONFIG_SETS["c2"]
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags)
+    llr = scpd.channel_generate(n, 32768, scpd.sigma(snr, k / n))
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr[:64].cpu().numpy(), threads=8)
+    seen = {}
+    for nfr in (32768, 2048):
+        out = dec.decode(llr[:nfr])
+        torch.cuda.synchronize()
+        seen[nfr] = dec.last_kernel_name
+        assert (out[:64].cpu().numpy().view(np.uint32) == want).all(), nfr
+    assert "slot-sliced" in seen[32768] and "int16x2" in seen[2048], seen
 
 
 def test_ragged_and_empty_batches(scpd):

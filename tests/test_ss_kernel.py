@@ -1,0 +1,89 @@
+"""CPU tier for the slot-sliced kernel (csrc/decode_ss.cuh, ss_plan.h): the kernel source executed lane by lane
+(tests/emu/ss_emu.cpp; fp16x2 emulated with exact float pairs, tensor memory as a per-lane array) against the oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sc_polar_decoder_hls_b200 as scpd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = {}
+
+
+def ss_emu(flags, n, par, q, ext, prune, llr, smem=18 * 1024, lsa=-1, lwin=-1, fuse=1, ltm=0):
+    if "l" not in _LIB:
+        _LIB["l"] = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libss_emu.so"))
+    out = np.zeros((len(llr), n // 32), np.uint32)
+    st = (ctypes.c_uint64 * 4)()
+    rc = _LIB["l"].ss_emu_decode(int(np.log2(n)), q, int(np.log2(par)), ext, prune, ol.P(flags), ol.P(llr),
+                                 ctypes.c_size_t(len(llr)), ol.P(out), ctypes.c_size_t(smem), lsa, lwin, fuse, st, ltm)
+    assert rc == 0, rc
+    return out, [int(v) for v in st]
+
+
+def _llrs(rng, n, k, q, nfr=26):
+    ma = (1 << (q - 1)) - 1
+    llr = ol.test_llrs(rng, n, nfr, k, maxabs=min(31, ma))
+    llr[-1][rng.random(n) < 0.5] = 0   # CA2 zeros: the all-information shortcut must fall back
+    llr[-2] = 0
+    wide = rng.integers(-ma, ma + 1, size=(8, n)).astype(np.int8)  # the whole range of the internal saturation
+    return np.concatenate([llr, wide])
+
+
+# (LLR_BITS, PAR, EXTENDED) instantiated in the emulator
+VARIANTS = [(8, 16, 1), (8, 16, 0), (6, 16, 1), (7, 16, 1), (8, 4, 1), (8, 8, 1), (6, 4, 0)]
+
+
+@pytest.mark.parametrize("name,n,k,q,par,ext", [("FB_N512_K256", 512, 256) + v for v in VARIANTS] +
+                         [("FB_N1024_K512", 1024, 512, 8, 16, 1)])
+def test_ss_kernel_source_against_oracle(name, n, k, q, par, ext):
+    """Plane arithmetic above 64 LLRs, plane -> fp16x2 transposition, the pattern-specialised 8-LLR routines, static
+    scale / saturation inside and outside the un-saturated leaf decoder, every pruning mode, ragged last task."""
+    flags = scpd.packed_flags(name, n)
+    llr = _llrs(np.random.default_rng(q * 100 + par + ext), n, k, q)
+    want = ol.decode_packed(n, par, q, 0, ext, flags, llr)
+    for prune in (0, 1, 2):
+        got, st = ss_emu(flags, n, par, q, ext, prune, llr)
+        assert (got == want).all(), prune
+    assert st[1] + st[2] > 0
+
+
+@pytest.mark.parametrize("lsa,lwin,ltm", [(-1, -1, 0), (7, 8, 8), (7, 9, 9), (6, 8, 8), (8, 10, 9), (7, 10, 0), (6, 8, 0),
+                                          (7, 9, 10), (6, 8, 11)])
+def test_ss_kernel_storage_plans(lsa, lwin, ltm):
+    """LLR levels in shared memory / tensor memory / workspace in every combination the planner can produce, partial
+    sums in the shared window or moved to the workspace (c2: N = 4096)."""
+    name, n, k = "frozen_n_4096_k_3072", 4096, 3072
+    flags = scpd.packed_flags(name, n)
+    llr = _llrs(np.random.default_rng(abs(lsa) * 10 + ltm), n, k, 8, nfr=10)
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+    for prune, fuse in ((0, 1), (2, 1), (2, 0)):   # fuse 0: no fused level-7 op in front of the 64-LLR nodes
+        got, _ = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=64 * 1024, lsa=lsa, lwin=lwin, ltm=ltm, fuse=fuse)
+        assert (got == want).all(), (prune, fuse)
+
+
+def test_ss_kernel_arbitrary_flag_tables():
+    """Flag tables no polar construction produces: the 8-LLR nodes run the run-time fallback of the walker."""
+    rng = np.random.default_rng(7)
+    for n in (128, 256, 1024):
+        for trial in range(3):
+            flags = (rng.random(n) < rng.random()).astype(np.uint8)
+            llr = rng.integers(-127, 128, size=(33, n)).astype(np.int8)
+            llr[rng.random(llr.shape) < 0.3] = 0
+            want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+            for prune in (0, 1, 2):
+                got, _ = ss_emu(flags, n, 16, 8, 1, prune, llr)
+                assert (got == want).all(), (n, trial, prune)
+
+
+def test_ss_known_patterns_cover_the_packaged_tables():
+    """The nine specialised 8-bit patterns are all that the packaged frozen tables contain (ss_plan.h, SS_KNOWN8)."""
+    known = {0x00, 0xFF, 0xFE, 0xE8, 0x80, 0xE0, 0xFC, 0xF8, 0xC0}
+    for name, n in (("FB_N1024_K512", 1024), ("frozen_n_4096_k_3072", 4096), ("frozen_n_32768_k_29492_snr_4_5", 32768),
+                    ("frozen_n_131072_k_117964", 131072), ("frozen_n_524288_k_262144", 524288)):
+        f = scpd.packed_flags(name, n).reshape(-1, 8)
+        pats = set(np.packbits(f, axis=1, bitorder="little").ravel().tolist())
+        assert pats <= known, (name, pats - known)

@@ -40,6 +40,25 @@ __device__ __forceinline__ void step(uint32_t (&v)[ILP]) {
         }
         if (OP == 13) asm volatile("mov.b32 %0, %1;" : "+r"(x) : "r"(y));
         if (OP == 14) asm volatile("sub.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
+        // round 2: the fp16x2 ops of the slot-sliced kernel's 32-LLR walker, and whether they co-issue with LOP3
+        if (OP == 15) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
+        if (OP == 16) asm volatile("add.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+        if (OP == 17) asm volatile("mul.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+        if (OP == 18) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+        if (OP == 19) {  // LOP3 + HFMA2 alternating
+            if (k & 1) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
+            else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(y), "r"(z));
+        }
+        if (OP == 20) {  // LOP3 + HADD2 alternating
+            if (k & 1) asm volatile("add.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+            else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(y), "r"(z));
+        }
+        if (OP == 21) asm volatile("and.b32 %0, %0, %1;" : "+r"(x) : "r"(y));  // two-input logic op
+        if (OP == 22) {  // 3 LOP3 : 1 HFMA2 (the kernel's mix is about 3 : 1)
+            if ((k & 3) == 3) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
+            else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(y), "r"(z));
+        }
+        if (OP == 23) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(*reinterpret_cast<float*>(&x)) : "f"(__uint_as_float(y)), "f"(__uint_as_float(z)));
     }
 }
 
@@ -101,5 +120,14 @@ int main() {
     run<7>("LOP3+VIMNMX", sms, clk, 32);
     run<10>("LOP3+SHF", sms, clk, 32);
     run<12>("LOP3+PRMT", sms, clk, 32);
+    run<21>("LOP (2 inputs)", sms, clk, 32);
+    run<15>("HFMA2", sms, clk, 32);
+    run<16>("HADD2", sms, clk, 32);
+    run<17>("HMUL2", sms, clk, 32);
+    run<18>("HMNMX2", sms, clk, 32);
+    run<23>("FFMA", sms, clk, 32);
+    run<19>("LOP3+HFMA2", sms, clk, 32);
+    run<20>("LOP3+HADD2", sms, clk, 32);
+    run<22>("3 LOP3 : 1 HFMA2", sms, clk, 32);
     return 0;
 }
