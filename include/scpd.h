@@ -107,6 +107,13 @@ int scpd_decode(scpd_decoder* dec, const int8_t* d_llr, size_t nframes, uint32_t
  * H2D copy / decode / D2H copy pipeline on three streams; returns when h_xhat is complete.
  * This is the call a host-only caller such as the reference testbench would make. */
 int scpd_decode_host(scpd_decoder* dec, const int8_t* h_llr, size_t nframes, uint32_t* h_xhat);
+/* Input contract of scpd_decode / scpd_decode_host: |llr| <= 2^(llr_bits-1) - 1.  The reference's quantiser alphabet is
+ * +-31 whatever LLR_BITS is (main.cpp:16-18); wider values up to the internal saturation are accepted.  Values outside
+ * that range (and -128) are NOT checked by the decode calls and give unspecified bits (the reference wraps them modulo
+ * 2^LLR_BITS on the sc_fifo<LLR> write, wrapper_in.h:33-34; only llr_bits = 5, where the +-31 alphabet itself wraps, is
+ * reproduced -- by the raw-pattern kernel).  scpd_validate_llr counts the offending values of a device batch
+ * (synchronous on `cuda_stream`). */
+int scpd_validate_llr(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint64_t* h_out_of_range, void* cuda_stream);
 /* Information-bit estimate u^ = x^ * F^(x)n (extra; the reference outputs x^ only). */
 int scpd_extract_info(scpd_decoder* dec, const uint32_t* d_xhat, size_t nframes, uint32_t* d_uhat,
                       void* cuda_stream);
@@ -140,6 +147,13 @@ typedef struct {
     uint64_t total_iterations;
 } scpd_stage_matrix;
 int scpd_stage_profile(const scpd_config* cfg, const uint8_t* h_info_flags, scpd_stage_matrix* out);
+/* The measured counterpart (sc_monitor.h:50-441 histograms cycles, not trips): scpd_stage_timing(d, 1) makes every later
+ * scpd_decode on the slot-sliced kernel add, for one warp (32 frames) per CTA, the SM-clock cycles between the fetch of a
+ * schedule op and the fetch of the next to cycles[function][level] (rows as SCPD_STAGE_*: F, G, H, R = a whole 64-LLR
+ * node incl. the level-7 f / g fused in front of it, R0, R1 = hard decision) and 1 to visits[function][level];
+ * scpd_stage_time reads and clears the histogram.  SCPD_E_UNSUPPORTED for handles without that kernel. */
+int scpd_stage_timing(scpd_decoder* d, int enable);
+int scpd_stage_time(scpd_decoder* d, uint64_t cycles[6][32], uint64_t visits[6][32]);
 
 /* ---- testbench harness on the device: src/testbench/ ---- */
 /* sigma = 1/sqrt(2 R 10^(EbN0/10)), main.cpp:91-98 (the reference hard-codes R = 0.5). */
@@ -147,7 +161,8 @@ float scpd_sigma(float ebn0_db, float rate);
 /* sc_xorshift128 (two streams, seed byte) -> sc_awgn (Box-Muller, 2 samples per draw) ->
  * sc_bpsk + sc_adder -> sc_quantizer.  Frame f of the stream uses draws [f*n/2, (f+1)*n/2) of
  * each generator, reached by GF(2) jump-ahead.  d_codeword: n bytes (0/1) shared by all frames
- * if per_frame == 0, [nframes][n] if 1, or NULL for the all-zero codeword (sc_encoder.h:105-110).
+ * if per_frame == 0, [nframes][n] if 1, packed rows [nframes][n/32] (LSB first) if 2, or NULL for the all-zero
+ * codeword (sc_encoder.h:105-110).
  * d_llr: [nframes][n] int8. */
 int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nframes, uint8_t seed,
                           float sigma, const uint8_t* d_codeword, int per_frame, int8_t* d_llr,
@@ -163,6 +178,16 @@ int scpd_count_errors(uint32_t n, size_t nframes, const uint32_t* d_xhat,
  * nframes frames starting at stream position first_frame, in batches; h_counters as above. */
 int scpd_run_ber(scpd_decoder* dec, float ebn0_db, float rate, uint64_t first_frame,
                  uint64_t nframes, uint8_t seed, const uint8_t* h_codeword, uint64_t h_counters[6]);
+/* The same loop with the other codeword sources and information-bit counters.
+ *   SCPD_SRC_CODEWORDS: h_codewords = ncw codewords of n bytes (0/1); frame g of the stream sends codeword g % ncw --
+ *     ncw = 3 with cw512x256 / cw1024x512 / cw8x4 is the reference's sc_encoder (sc_encoder.h:91-113); NULL / 0 = all-zero.
+ *   SCPD_SRC_RANDOM: K random information bits per frame (counter-based generator keyed by payload_seed and the frame
+ *     index; the reference has no payload source), encoded on the device: x = u F^(x)n, natural order.
+ * counters[0..5] as scpd_count_errors (codeword bits: what sc_error_counter.h:68-125 counts); counters[6..9] on the
+ * information positions of u^ = x^ F^(x)n: bit errors, frames in error, bits (k per frame), frames. */
+enum { SCPD_SRC_CODEWORDS = 0, SCPD_SRC_RANDOM = 1 };
+int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint64_t first_frame, uint64_t nframes, uint8_t seed,
+                    int src_mode, const uint8_t* h_codewords, uint32_t ncw, uint64_t payload_seed, uint64_t h_counters[10]);
 
 const char* scpd_last_error(void);
 const char* scpd_status_string(int status);

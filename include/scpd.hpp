@@ -74,6 +74,14 @@ public:
         check(scpd_run_ber(h_, ebn0_db, rate, first_frame, nframes, seed, codeword, c));
         return BerCounters{c[0], c[1], c[2], c[3], c[4], c[5]};
     }
+    // the other codeword sources (stored codewords in turn, random payloads) and the information-bit counters:
+    // c[0..5] codeword bits as run_ber, c[6..9] information bits (errors, frames in error, bits, frames)
+    std::vector<uint64_t> run_ber_ex(float ebn0_db, float rate, uint64_t nframes, uint64_t first_frame, uint8_t seed, int src_mode,
+                                     const uint8_t* codewords, uint32_t ncw, uint64_t payload_seed) {
+        std::vector<uint64_t> c(10);
+        check(scpd_run_ber_ex(h_, ebn0_db, rate, first_frame, nframes, seed, src_mode, codewords, ncw, payload_seed, c.data()));
+        return c;
+    }
     // measurement aids (sc_monitor's role): duration of the tree-walk kernel of the last decode, kernel in use
     void kernel_timing(bool on) { check(scpd_kernel_timing(h_, on ? 1 : 0)); }
     float last_kernel_ms() {

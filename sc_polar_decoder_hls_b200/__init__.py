@@ -58,6 +58,7 @@ def _load():
         "scpd_destroy": (None, [vp]),
         "scpd_decode": (c.c_int, [vp, vp, c.c_size_t, vp, vp]),
         "scpd_decode_host": (c.c_int, [vp, vp, c.c_size_t, vp]),
+        "scpd_validate_llr": (c.c_int, [vp, vp, c.c_size_t, c.POINTER(c.c_uint64), vp]),
         "scpd_extract_info": (c.c_int, [vp, vp, c.c_size_t, vp, vp]),
         "scpd_get_config": (c.c_int, [vp, c.POINTER(Config)]),
         "scpd_schedule_stats": (c.c_int, [vp, c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]),
@@ -73,6 +74,10 @@ def _load():
         "scpd_count_errors": (c.c_int, [c.c_uint32, c.c_size_t, vp, vp, c.c_int, vp, vp]),
         "scpd_run_ber": (c.c_int, [vp, c.c_float, c.c_float, c.c_uint64, c.c_uint64, c.c_uint8, u8p,
                                    c.POINTER(c.c_uint64)]),
+        "scpd_run_ber_ex": (c.c_int, [vp, c.c_float, c.c_float, c.c_uint64, c.c_uint64, c.c_uint8, c.c_int, u8p, c.c_uint32,
+                                      c.c_uint64, c.POINTER(c.c_uint64)]),
+        "scpd_stage_timing": (c.c_int, [vp, c.c_int]),
+        "scpd_stage_time": (c.c_int, [vp, vp, vp]),
         "scpd_last_error": (c.c_char_p, []),
         "scpd_status_string": (c.c_char_p, [c.c_int]),
     }
@@ -86,10 +91,12 @@ def _load():
 lib = _load()
 EXPORTS = ["scpd_frozen_load_order", "scpd_frozen_load_flags", "scpd_frozen_write_order",
            "scpd_frozen_write_flags", "scpd_write_polar_parameters", "scpd_create", "scpd_destroy",
-           "scpd_decode", "scpd_decode_host", "scpd_extract_info", "scpd_get_config",
+           "scpd_decode", "scpd_decode_host", "scpd_validate_llr", "scpd_extract_info", "scpd_get_config",
            "scpd_schedule_stats", "scpd_launch_count", "scpd_kernel_timing", "scpd_last_kernel_ms",
            "scpd_kernel_name", "scpd_last_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate",
-           "scpd_count_errors", "scpd_run_ber", "scpd_last_error", "scpd_status_string"]
+           "scpd_count_errors", "scpd_run_ber", "scpd_run_ber_ex", "scpd_stage_timing", "scpd_stage_time", "scpd_last_error",
+           "scpd_status_string"]
+SRC_CODEWORDS, SRC_RANDOM = 0, 1
 
 
 def check(status):
@@ -198,6 +205,14 @@ class Decoder:
         check(lib.scpd_decode_host(self._h, _np_ptr(llr), llr.shape[0], _np_ptr(out)))
         return out
 
+    def validate_llr(self, llr):
+        """Number of LLRs of a CUDA int8 batch outside the input contract |llr| <= 2^(llr_bits-1) - 1."""
+        import torch
+        out = ctypes.c_uint64()
+        s = torch.cuda.current_stream(llr.device).cuda_stream
+        check(lib.scpd_validate_llr(self._h, llr.data_ptr(), llr.shape[0], ctypes.byref(out), s))
+        return int(out.value)
+
     def extract_info(self, xhat, stream=None):
         import torch
         out = torch.empty_like(xhat)
@@ -242,6 +257,49 @@ class Decoder:
         check(lib.scpd_run_ber(self._h, ebn0_db, rate, first_frame, nframes, seed, cw, cnt))
         return [int(v) for v in cnt]
 
+    def run_ber_ex(self, ebn0_db, rate, nframes, first_frame=0, seed=0xF0, codewords=None, random_payload=False,
+                   payload_seed=1):
+        """scpd_run_ber_ex: codewords [ncw, n] sent in turn (the reference's sc_encoder with ncw = 3), or random
+        information words encoded on the device; ten counters (codeword bits, then information bits)."""
+        cnt = (ctypes.c_uint64 * 10)()
+        cw, ncw = None, 0
+        if codewords is not None:
+            cwa = np.ascontiguousarray(np.atleast_2d(codewords), np.uint8)
+            cw, ncw = _np_ptr(cwa), cwa.shape[0]
+        check(lib.scpd_run_ber_ex(self._h, ebn0_db, rate, first_frame, nframes, seed,
+                                  SRC_RANDOM if random_payload else SRC_CODEWORDS, cw, ncw, payload_seed, cnt))
+        return [int(v) for v in cnt]
+
+    def stage_timing(self, enable=True):
+        check(lib.scpd_stage_timing(self._h, 1 if enable else 0))
+
+    def stage_time(self):
+        """(cycles, visits): uint64 [6, 32] per (function, level) since the last call (scpd_stage_time)."""
+        cyc, vis = np.zeros((6, 32), np.uint64), np.zeros((6, 32), np.uint64)
+        check(lib.scpd_stage_time(self._h, _np_ptr(cyc), _np_ptr(vis)))
+        return cyc, vis
+
+
+def payload_words(seed, first_frame, nframes, info_flags):
+    """Host restatement of the device payload source of scpd_run_ber_ex (harness.cuh: payload_word): uint32
+    [nframes, n/32] information words, frozen positions 0."""
+    n = len(info_flags)
+    wpf = max(1, n // 32)
+    m64 = (1 << 64) - 1
+    f = (np.arange(nframes, dtype=np.uint64) + np.uint64(first_frame))[:, None]
+    w = np.arange(wpf, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        z = (np.uint64((seed * 0x9E3779B97F4A7C15) & m64) + f * np.uint64(0xBF58476D1CE4E5B9) + w * np.uint64(0x94D049BB133111EB))
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    flags = np.zeros(wpf * 32, np.uint8)
+    flags[:n] = info_flags
+    mask = np.packbits(flags, bitorder="little").view(np.uint32)
+    return (z & np.uint64(0xFFFFFFFF)).astype(np.uint32) & mask[None, :]
+
 
 def channel_generate(n, nframes, sigma_v, first_frame=0, seed=0xF0, codeword=None, device=0, stream=None):
     """Device channel (scpd_channel_generate) -> torch int8 [nframes, n]."""
@@ -251,7 +309,7 @@ def channel_generate(n, nframes, sigma_v, first_frame=0, seed=0xF0, codeword=Non
     cw_ptr, per_frame = None, 0
     if codeword is not None:
         cw = torch.as_tensor(np.ascontiguousarray(codeword, np.uint8)).to(dev)
-        per_frame = 1 if cw.dim() == 2 else 0
+        per_frame = 1 if cw.dim() == 2 else 0  # (packed rows, mode 2, are an internal format of scpd_run_ber_ex)
         cw_ptr = cw.data_ptr()
     s = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
     with torch.cuda.device(dev):

@@ -73,6 +73,8 @@ struct SsParams {
     unsigned long long ws_stride;  // uint4 per warp
     uint32_t ws_beta_off;
     uint32_t aoff[24];
+    // != nullptr: per (function, level) SM-clock cycles [6][32] and visits [6][32] of warp 0 of every CTA (scpd_stage_time)
+    unsigned long long* prof;
 };
 
 namespace ss {
@@ -782,11 +784,31 @@ struct SsThread {
         sub64(wd, r0, r1, !xs, d0, sched[pc + 2], sched[pc + 3], sched[pc + 4]);
     }
 
+    bool prof_on = false;
+    uint32_t prof_fn = 6u, prof_l = 0u;
+    long long prof_t0 = 0;
     SS_DEV void run() {
         uint32_t pc = 0;
+        prof_fn = 6u;
         for (;;) {
             const uint32_t w = sched[pc];
             const uint32_t code = ss_op_code(w), l = ss_op_level(w), wd = ss_op_word(w);
+#if defined(__CUDA_ARCH__)
+            // measured counterpart of the reference's function x level monitor (sc_monitor.h:50-441): cycles between
+            // the fetch of this op and the fetch of the next, for one warp per CTA
+            if (prof_on) {
+                const long long now = clock64();
+                if (prof_fn < 6u && (threadIdx.x & 31u) == 0u) {
+                    atomicAdd(p.prof + prof_fn * 32u + prof_l, (unsigned long long)(now - prof_t0));
+                    atomicAdd(p.prof + 192u + prof_fn * 32u + prof_l, 1ull);
+                }
+                // rows: 0 F, 1 G (g and g0), 2 H, 3 R (64-LLR node incl. a fused level-7 op), 4 R0, 5 R1 (hard decision)
+                prof_fn = code == SS_F ? 0u : (code == SS_G || code == SS_G0) ? 1u : (code == SS_H || code == SS_HCOPY) ? 2u
+                          : (code == SS_SUB || code == SS_XS) ? 3u : code == SS_R0 ? 4u : code == SS_R1 ? 5u : 6u;
+                prof_l = (code == SS_SUB || code == SS_XS) ? 6u : l;
+                prof_t0 = clock64();
+            }
+#endif
             switch (code) {
                 case SS_END: return;
                 case SS_F:
@@ -912,6 +934,7 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     } else {
         t.sched = p.sched;
     }
+    t.prof_on = p.prof != nullptr && warp == 0;
     const unsigned long long slot_id = (unsigned long long)blockIdx.x * nwarps + warp;
     t.wsl = p.ws + slot_id * p.ws_stride + lane;
     for (unsigned long long task = slot_id; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {

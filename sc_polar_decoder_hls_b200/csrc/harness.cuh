@@ -144,10 +144,17 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
             float s0 = 1.0f, s1 = 1.0f;  // sc_bpsk.h:53
             if (codeword) {
                 const unsigned long long i = i0 + 2u * k;
-                const uint8_t* cw = per_frame ? codeword + (f0 + i / n) * n : codeword;
                 const uint32_t pos = (uint32_t)i & nmask;
-                s0 = cw[pos] ? -1.0f : 1.0f;
-                s1 = cw[pos + 1] ? -1.0f : 1.0f;
+                if (per_frame == 2) {  // packed rows [frame][n / 32] (the reference words scpd_run_ber_ex builds on the device)
+                    const uint32_t* row = reinterpret_cast<const uint32_t*>(codeword) + (f0 + i / n) * (n >= 32u ? n / 32u : 1u);
+                    const uint32_t wv = row[pos >> 5] >> (pos & 31u);
+                    s0 = (wv & 1u) ? -1.0f : 1.0f;
+                    s1 = (wv & 2u) ? -1.0f : 1.0f;
+                } else {
+                    const uint8_t* cw = per_frame ? codeword + (f0 + i / n) * n : codeword;
+                    s0 = cw[pos] ? -1.0f : 1.0f;
+                    s1 = cw[pos + 1] ? -1.0f : 1.0f;
+                }
             }
             const int q0 = quantize_llr(__fadd_rn(s0, __fmul_rn(ph, sigma)));  // sc_adder.h:139-140
             const int q1 = quantize_llr(__fadd_rn(s1, __fmul_rn(qu, sigma)));
@@ -197,6 +204,102 @@ count_errors_kernel(uint32_t wpf, uint32_t n, unsigned long long nframes, const 
         atomicAdd(counters + 3, nf);
         atomicAdd(counters + 4, bew);
         atomicAdd(counters + 5, few);
+    }
+}
+
+// ---------------------------------------------------------------- input contract check
+// counts the LLRs outside +-limit (16 bytes per thread and trip); the decode kernels assume |llr| <= 2^(Q-1) - 1
+__global__ void __launch_bounds__(256)
+count_out_of_range_kernel(const int8_t* __restrict__ llr, unsigned long long nbytes, int limit, unsigned long long* __restrict__ count) {
+    unsigned long long bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const bool al = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
+    const unsigned long long nvec = al ? nbytes / 16 : 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(llr) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int x = (int)(int8_t)(w[k] >> (8 * b));
+                bad += (x > limit || x < -limit);
+            }
+    }
+    for (unsigned long long i = nvec * 16 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
+        const int x = llr[i];
+        bad += (x > limit || x < -limit);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) bad += __shfl_xor_sync(0xFFFFFFFFu, bad, off);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+
+// ---------------------------------------------------------------- codeword sources of scpd_run_ber_ex
+// ref[f] = packed codeword (first_frame + f) % ncw of `cws` ([ncw][wpf] words): the reference's sc_encoder replays its
+// stored codewords in turn (sc_encoder.h:91-113: j = 0, 1, 2, 0, ...)
+__global__ void __launch_bounds__(256)
+ref_cycle_kernel(uint32_t wpf, unsigned long long first_frame, unsigned long long nframes, const uint32_t* __restrict__ cws,
+                 uint32_t ncw, uint32_t* __restrict__ ref) {
+    const unsigned long long total = nframes * wpf;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long f = i / wpf;
+        ref[i] = cws[((first_frame + f) % ncw) * wpf + (uint32_t)(i % wpf)];
+    }
+}
+// u[f] = random information word of frame first_frame + f: 32 bits per word from a counter-based generator
+// (splitmix64 finaliser over (payload_seed, frame, word)), masked with the information flags; frozen positions are 0.
+// The reference has no payload source; this one is ours and is restated in tests/ for the checks.
+__device__ __forceinline__ uint32_t payload_word(unsigned long long seed, unsigned long long frame, uint32_t w) {
+    unsigned long long z = seed * 0x9E3779B97F4A7C15ull + frame * 0xBF58476D1CE4E5B9ull + (unsigned long long)w * 0x94D049BB133111EBull;
+    z ^= z >> 30;
+    z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27;
+    z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)z;
+}
+__global__ void __launch_bounds__(256)
+payload_kernel(uint32_t wpf, unsigned long long first_frame, unsigned long long nframes, unsigned long long seed,
+               const uint32_t* __restrict__ info_mask, uint32_t* __restrict__ u) {
+    const unsigned long long total = nframes * wpf;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long f = i / wpf;
+        const uint32_t w = (uint32_t)(i % wpf);
+        u[i] = payload_word(seed, first_frame + f, w) & info_mask[w];
+    }
+}
+__global__ void __launch_bounds__(256)
+xor_words_kernel(unsigned long long total, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = a[i] ^ b[i];
+}
+// information-bit errors: d = (x^ ^ x) F^(x)n = u^ ^ u (the transform is linear and its own inverse); counters[0] +=
+// popcount(d & info mask), [1] += frames with any, [2] += k per frame, [3] += frames
+__global__ void __launch_bounds__(256)
+count_info_kernel(uint32_t wpf, uint32_t k, unsigned long long nframes, const uint32_t* __restrict__ d,
+                  const uint32_t* __restrict__ info_mask, unsigned long long* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    unsigned long long be = 0, fe = 0, nf = 0;
+    for (unsigned long long f = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < nframes;
+         f += wstride) {
+        uint32_t e = 0;
+        for (uint32_t w = lane; w < wpf; w += 32) e += __popc(d[f * wpf + w] & info_mask[w]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, off);
+        be += e;
+        fe += (e != 0);
+        nf += 1;
+    }
+    if (lane == 0 && nf) {
+        atomicAdd(counters + 0, be);
+        atomicAdd(counters + 1, fe);
+        atomicAdd(counters + 2, nf * k);
+        atomicAdd(counters + 3, nf);
     }
 }
 

@@ -119,6 +119,7 @@ struct scpd_decoder {
     int log2n = 0, log2par = 0;
     uint32_t wpf = 1;
     std::vector<uint32_t> sched_host;
+    std::vector<uint8_t> info_flags;  // the frozen table the handle was created with (1 = information bit)
     ScheduleStats stats;
     uint32_t* d_sched = nullptr;
     // generic-kernel layout
@@ -142,6 +143,11 @@ struct scpd_decoder {
     int bs_group = 8, bs_warps = 2, bs_ctas_per_sm = 1;
     bool bs_sched_smem = false;
     bool kernel_pinned = false;  // SCPD_KERNEL was set when the handle was created
+    // test / profiling overrides, read once in scpd_create (INTEGRATION.md lists them): nothing reads the environment later
+    unsigned fast_wide_lanes = 256;
+    uint32_t bs_prefetch = 0;
+    unsigned long long bs_min_groups = 0;
+    size_t host_chunk_mb = 256;
     BsPlan bs_plan;
     std::vector<uint32_t> bs_sched_host;
     ScheduleStats bs_stats;
@@ -165,6 +171,7 @@ struct scpd_decoder {
     size_t ss_ws_bytes = 0;
     uint4* d_ss_planes = nullptr;
     size_t ss_planes_bytes = 0;
+    unsigned long long* d_ss_prof = nullptr;  // scpd_stage_timing: [2][6][32] cycles / visits
     // raw-pattern kernel plan (decode_raw.cuh): the configurations outside the in-range int16x2 / bit-sliced
     // datapaths.  raw_only: it is the only kernel of this handle
     bool raw_ok = false, raw_only = false;
@@ -191,6 +198,11 @@ struct scpd_decoder {
     uint32_t* d_xhat = nullptr;
     size_t stage_frames = 0;
     unsigned long long* d_counters = nullptr;
+    // scratch of scpd_run_ber_ex, kept between calls: per-frame reference words (double-buffered), difference words,
+    // information mask, ten counters
+    uint32_t *d_ber_ref[2] = {nullptr, nullptr}, *d_ber_diff = nullptr, *d_ber_mask = nullptr;
+    size_t ber_ref_bytes[2] = {0, 0}, ber_diff_bytes = 0;
+    unsigned long long* d_ber_cnt = nullptr;
     uint64_t launches = 0;
     char last_kernel[96] = "";  // what the last scpd_decode launched (scpd_last_kernel_name)
 };
@@ -471,7 +483,7 @@ static int plan_fast(scpd_decoder* d, const uint8_t* flags) {
 // GPU's lanes idle (measured, profiles/tuning_r1.md: N = 2^19, 1024 frames: 5.8 / 11.0 Gb/s with 8 / 16 lanes).
 static const FastPlan& pick_fast(const scpd_decoder* d, unsigned long long num_fp) {
     const FastPlan* best = &d->fast;
-    const unsigned long long lanes_wanted = (unsigned long long)d->num_sms * (unsigned)env_int("SCPD_FAST_WIDE_LANES", 256);
+    const unsigned long long lanes_wanted = (unsigned long long)d->num_sms * d->fast_wide_lanes;
     for (const FastPlan& w : d->fast_wide)
         if (num_fp * (unsigned)(best->coop ? 32 * best->coop : best->group) < lanes_wanted) best = &w;
     return *best;
@@ -586,6 +598,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     scpd_decoder* d = new (std::nothrow) scpd_decoder();
     if (!d) return set_error(SCPD_E_NOMEM, "out of host memory");
     d->cfg = *cfg;
+    d->info_flags.assign(flags, flags + n);
     d->device = device;
     d->log2n = ilog2(n);
     d->log2par = log2par;
@@ -599,6 +612,11 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     }
     d->num_sms = prop.multiProcessorCount;
     d->kernel_pinned = std::getenv("SCPD_KERNEL") != nullptr;
+    d->fast_wide_lanes = (unsigned)env_int("SCPD_FAST_WIDE_LANES", 256);
+    // measured: +5 % at N = 1024 (latency of the read-back), -2 % at N = 4096 (already short of DRAM bandwidth)
+    d->bs_prefetch = (uint32_t)env_int("SCPD_BS_PREFETCH", d->log2n <= 11 ? 1 : 0);
+    d->bs_min_groups = (unsigned long long)env_int("SCPD_BS_MIN_GROUPS", d->log2n <= 11 ? 1536 : d->log2n <= 13 ? 768 : d->log2n <= 17 ? 512 : 256);
+    d->host_chunk_mb = (size_t)env_int("SCPD_HOST_CHUNK_MB", 256);
     d->raw_only = raw_only;
     int rc = SCPD_OK;
     if (!raw_only) {
@@ -671,6 +689,7 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_ss_sched);
     cudaFree(d->d_ss_ws);
     cudaFree(d->d_ss_planes);
+    cudaFree(d->d_ss_prof);
     for (int b = 0; b < 2; b++) {
         cudaFree(d->d_llr2[b]);
         cudaFree(d->d_xhat2[b]);
@@ -686,6 +705,11 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_llr);
     cudaFree(d->d_xhat);
     cudaFree(d->d_counters);
+    cudaFree(d->d_ber_ref[0]);
+    cudaFree(d->d_ber_ref[1]);
+    cudaFree(d->d_ber_diff);
+    cudaFree(d->d_ber_mask);
+    cudaFree(d->d_ber_cnt);
     delete d;
 }
 
@@ -792,8 +816,7 @@ static int decode_bs(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.ws_stride = d->bs_plan.ws_stride;
     p.ws_beta_off = d->bs_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->bs_plan.aoff[l];
-    // measured: +5 % at N = 1024 (latency of the read-back), -2 % at N = 4096 (already short of DRAM bandwidth)
-    p.prefetch = (uint32_t)env_int("SCPD_BS_PREFETCH", d->log2n <= 11 ? 1 : 0);
+    p.prefetch = d->bs_prefetch;
     bs_kernel_t k = bs_kernel_ptr((int)d->cfg.format, (int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->bs_group);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(d->bs_warps * 32)), d->bs_smem_bytes, st>>>(p);
@@ -849,6 +872,7 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.ws_stride = d->ss_plan.ws_stride;
     p.ws_beta_off = d->ss_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->ss_plan.aoff[l];
+    p.prof = d->d_ss_prof;
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
@@ -915,8 +939,7 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     // GPU; below the measured crossover (profiles/tuning_r1.md: about 49 k frames at N = 1024, 24 k at N = 4096,
     // 16 k at N = 32768 and 131072, 8 k at N = 2^19) the int16x2 kernel is faster: 2 frames per lane group, and
     // lane groups that widen to 16 / 32 lanes as the batch shrinks (pick_fast).
-    const unsigned long long bs_min_groups = (unsigned long long)env_int(
-        "SCPD_BS_MIN_GROUPS", d->log2n <= 11 ? 1536 : d->log2n <= 13 ? 768 : d->log2n <= 17 ? 512 : 256);
+    const unsigned long long bs_min_groups = d->bs_min_groups;
     const bool bs_small = d->fast.group && d->cfg.format == SCPD_FMT_CA2 && !d->kernel_pinned &&
                           (nframes + 31) / 32 < bs_min_groups;
     if (d->bs_ok && !bs_small && (reinterpret_cast<uintptr_t>(d_llr) & 3u) == 0)
@@ -1014,7 +1037,7 @@ extern "C" int scpd_decode_host(scpd_decoder* d, const int8_t* h_llr, size_t nfr
     if (!h_llr || !h_xhat) return set_error(SCPD_E_ARG, "scpd_decode_host: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
     const size_t n = d->cfg.n, row_out = (size_t)d->wpf * 4;
-    size_t chunk = ((size_t)env_int("SCPD_HOST_CHUNK_MB", 256) << 20) / n;
+    size_t chunk = (d->host_chunk_mb << 20) / n;
     chunk = std::max<size_t>(chunk, (size_t)64 * 32 * (size_t)d->num_sms / 16);  // >= 4 frame groups per SM per chunk
     chunk = std::max<size_t>(32, chunk & ~(size_t)31);
     if (chunk > nframes) chunk = nframes;
@@ -1098,6 +1121,61 @@ extern "C" int scpd_extract_info(scpd_decoder* d, const uint32_t* d_xhat, size_t
     return SCPD_OK;
 }
 
+// Measured function x level matrix: with timing on, warp 0 of every CTA of the slot-sliced kernel adds the
+// SM-clock cycles it spends in each schedule op to a [function][level] histogram.
+extern "C" int scpd_stage_timing(scpd_decoder* d, int enable) {
+    if (!d) return set_error(SCPD_E_ARG, "scpd_stage_timing: null decoder");
+    if (!d->ss_ok) return set_error(SCPD_E_UNSUPPORTED, "scpd_stage_timing: only the slot-sliced kernel measures per-stage time");
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (enable && !d->d_ss_prof) {
+        CUDA_TRY(cudaMalloc(&d->d_ss_prof, 2 * 6 * 32 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(d->d_ss_prof, 0, 2 * 6 * 32 * sizeof(unsigned long long)));
+    } else if (!enable && d->d_ss_prof) {
+        cudaFree(d->d_ss_prof);
+        d->d_ss_prof = nullptr;
+    }
+    return SCPD_OK;
+}
+extern "C" int scpd_stage_time(scpd_decoder* d, uint64_t cycles[6][32], uint64_t visits[6][32]) {
+    if (!d || !cycles || !visits) return set_error(SCPD_E_ARG, "scpd_stage_time: null argument");
+    if (!d->d_ss_prof) return set_error(SCPD_E_ARG, "scpd_stage_time: timing is off (scpd_stage_timing)");
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(2 * 6 * 32);
+    CUDA_TRY(cudaMemcpy(h.data(), d->d_ss_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(d->d_ss_prof, 0, h.size() * sizeof(unsigned long long)));
+    for (int f = 0; f < 6; f++)
+        for (int l = 0; l < 32; l++) {
+            cycles[f][l] = h[f * 32 + l];
+            visits[f][l] = h[192 + f * 32 + l];
+        }
+    return SCPD_OK;
+}
+
+// Input contract of scpd_decode: |llr| <= 2^(LLR_BITS-1) - 1 (the reference's quantiser alphabet is +-31 whatever
+// LLR_BITS is, main.cpp:16-18; wider inputs up to the internal saturation are accepted).  Values outside are undefined
+// behaviour in the fast kernels -- they keep them as they are or drop high magnitude bits, depending on the kernel --
+// and wrap modulo 2^LLR_BITS in the reference (wrapper_in.h:33-34); this pass lets an integrator check a batch.
+extern "C" int scpd_validate_llr(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint64_t* h_out_of_range, void* stream) {
+    if (!d || !h_out_of_range) return set_error(SCPD_E_ARG, "scpd_validate_llr: null argument");
+    *h_out_of_range = 0;
+    if (nframes == 0) return SCPD_OK;
+    if (!d_llr) return set_error(SCPD_E_ARG, "scpd_validate_llr: null buffer");
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(d->d_counters, 0, sizeof(unsigned long long), st));
+    const int limit = (1 << (d->cfg.llr_bits - 1)) - 1;
+    count_out_of_range_kernel<<<(unsigned)d->num_sms * 8u, 256, 0, st>>>(d_llr, (unsigned long long)nframes * d->cfg.n, limit, d->d_counters);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, d->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *h_out_of_range = h;
+    d->launches++;
+    return SCPD_OK;
+}
+
 extern "C" int scpd_get_config(const scpd_decoder* d, scpd_config* out) {
     if (!d || !out) return set_error(SCPD_E_ARG, "scpd_get_config: null argument");
     *out = d->cfg;
@@ -1160,65 +1238,150 @@ extern "C" int scpd_count_errors(uint32_t n, size_t nframes, const uint32_t* d_x
     return SCPD_OK;
 }
 
-// Monte-Carlo loop on the device: generate -> decode -> count, batch after batch.  Generation of batch i + 1 runs on a
-// second stream while batch i is decoded and counted (double-buffered LLR / x^ staging), so the SFU-bound channel
-// kernel overlaps the LOP3-bound decode.
-extern "C" int scpd_run_ber(scpd_decoder* d, float ebn0_db, float rate, uint64_t first_frame, uint64_t nframes,
-                            uint8_t seed, const uint8_t* h_codeword, uint64_t h_counters[6]) {
-    if (!d || !h_counters) return set_error(SCPD_E_ARG, "scpd_run_ber: null argument");
+// Monte-Carlo loop on the device: source -> channel -> decode -> count, batch after batch.  Generation of batch i + 1
+// runs on a second stream while batch i is decoded and counted (double-buffered staging).
+//   src_mode SCPD_SRC_CODEWORDS: h_codewords = ncw codewords of n bytes (0/1); frame g of the stream sends codeword
+//            g % ncw (ncw = 3 is the reference's sc_encoder for N in {8, 512, 1024}, sc_encoder.h:91-113); ncw = 0 /
+//            NULL: the all-zero codeword (what the reference sends for any other N, :105-110)
+//   src_mode SCPD_SRC_RANDOM: K random information bits per frame, encoded on the device (x = u F^(x)n, natural
+//            order, frozen positions 0)
+// counters[0..5] as scpd_count_errors (codeword bits, what the reference counts); [6..9] information bits:
+// errors, frames in error, bits, frames (u^ = x^ F^(x)n on the information positions).
+extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint64_t first_frame, uint64_t nframes,
+                               uint8_t seed, int src_mode, const uint8_t* h_codewords, uint32_t ncw, uint64_t payload_seed,
+                               uint64_t h_counters[10]) {
+    if (!d || !h_counters) return set_error(SCPD_E_ARG, "scpd_run_ber_ex: null argument");
+    if (src_mode != SCPD_SRC_CODEWORDS && src_mode != SCPD_SRC_RANDOM) return set_error(SCPD_E_ARG, "scpd_run_ber_ex: unknown source mode");
+    if (src_mode == SCPD_SRC_CODEWORDS && (!h_codewords || ncw == 0)) {
+        h_codewords = nullptr;
+        ncw = 0;
+    }
     CUDA_TRY(cudaSetDevice(d->device));
-    const uint32_t n = d->cfg.n;
+    const uint32_t n = d->cfg.n, wpf = d->wpf;
+    std::memset(h_counters, 0, 10 * sizeof(uint64_t));
     // batch so that LLR staging stays around 0.5 GiB per buffer, but never fewer than 8 tasks of 32 frames per SM
     size_t batch = (size_t)((1ull << 29) / n);
     batch = std::max<size_t>(batch, (size_t)8 * 32 * (size_t)d->num_sms);
     batch &= ~(size_t)31;
     if (batch > nframes) batch = (size_t)nframes;
-    if (batch == 0) {
-        std::memset(h_counters, 0, 6 * sizeof(uint64_t));
-        return SCPD_OK;
-    }
+    if (batch == 0) return SCPD_OK;
     int rc = ensure_pipeline(d, batch);
     if (rc) return rc;
-    struct Tmp {  // freed on every exit
+    const bool per_frame_ref = src_mode == SCPD_SRC_RANDOM || ncw > 1;
+    struct Tmp {  // small per-call buffers, freed on every exit; the large scratch lives in the handle
         uint8_t* cw = nullptr;
-        uint32_t* ref = nullptr;
+        uint32_t* cws = nullptr;
         ~Tmp() {
             cudaFree(cw);
-            cudaFree(ref);
+            cudaFree(cws);
         }
+        uint32_t *mask = nullptr, *ref[2] = {nullptr, nullptr}, *diff = nullptr;
+        unsigned long long* cnt = nullptr;
     } tmp;
-    if (h_codeword) {
-        std::vector<uint32_t> ref(d->wpf, 0);
+    auto keep = [](void** ptr, size_t* have, size_t need) -> cudaError_t {  // grow a handle-owned buffer (synchronous)
+        if (need <= *have) return cudaSuccess;
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        *have = 0;
+        const cudaError_t e = cudaMalloc(ptr, need);
+        if (e == cudaSuccess) *have = need;
+        return e;
+    };
+    if (!d->d_ber_cnt) CUDA_TRY(cudaMalloc(&d->d_ber_cnt, 10 * sizeof(unsigned long long)));
+    tmp.cnt = d->d_ber_cnt;
+    if (!d->d_ber_mask) {  // information mask (packed flags) for the information-bit counters and the payload source
+        std::vector<uint32_t> mask(wpf, 0);
         for (uint32_t i = 0; i < n; i++)
-            if (h_codeword[i] & 1) ref[i >> 5] |= 1u << (i & 31);
-        CUDA_TRY(cudaMalloc(&tmp.cw, n));
-        CUDA_TRY(cudaMalloc(&tmp.ref, d->wpf * 4));
-        CUDA_TRY(cudaMemcpy(tmp.cw, h_codeword, n, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(tmp.ref, ref.data(), d->wpf * 4, cudaMemcpyHostToDevice));
+            if (d->info_flags[i]) mask[i >> 5] |= 1u << (i & 31);
+        CUDA_TRY(cudaMalloc(&d->d_ber_mask, wpf * 4));
+        CUDA_TRY(cudaMemcpy(d->d_ber_mask, mask.data(), wpf * 4, cudaMemcpyHostToDevice));
     }
+    tmp.mask = d->d_ber_mask;
+    if (ncw >= 1) {
+        std::vector<uint32_t> packed((size_t)ncw * wpf, 0);
+        for (uint32_t j = 0; j < ncw; j++)
+            for (uint32_t i = 0; i < n; i++)
+                if (h_codewords[(size_t)j * n + i] & 1) packed[(size_t)j * wpf + (i >> 5)] |= 1u << (i & 31);
+        CUDA_TRY(cudaMalloc(&tmp.cws, packed.size() * 4));
+        CUDA_TRY(cudaMemcpy(tmp.cws, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+        if (ncw == 1) {
+            CUDA_TRY(cudaMalloc(&tmp.cw, n));
+            CUDA_TRY(cudaMemcpy(tmp.cw, h_codewords, n, cudaMemcpyHostToDevice));
+        }
+    }
+    if (per_frame_ref)
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(keep((void**)&d->d_ber_ref[b], &d->ber_ref_bytes[b], batch * (size_t)wpf * 4));
+            tmp.ref[b] = d->d_ber_ref[b];
+        }
+    CUDA_TRY(keep((void**)&d->d_ber_diff, &d->ber_diff_bytes, batch * (size_t)wpf * 4));
+    tmp.diff = d->d_ber_diff;
     cudaStream_t sg = d->st_in, sd = d->st_comp;  // generator stream, decode + count stream
-    CUDA_TRY(cudaMemsetAsync(d->d_counters, 0, 6 * sizeof(unsigned long long), sd));
+    CUDA_TRY(cudaMemsetAsync(tmp.cnt, 0, 10 * sizeof(unsigned long long), sd));
     const float sigma = scpd_sigma(ebn0_db, rate);
+    const unsigned gblocks = (unsigned)d->num_sms * 8u;
     size_t i = 0;
     for (uint64_t done = 0; done < nframes && rc == SCPD_OK; done += batch, i++) {
         const int b = (int)(i & 1);
         const size_t nb = (size_t)((nframes - done < batch) ? nframes - done : batch);
-        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(sg, d->ev_dec[b], 0));  // decode i - 2 has consumed this LLR buffer
-        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, tmp.cw, 0, d->d_llr2[b], sg);
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(sg, d->ev_out[b], 0));  // batch i - 2 has been decoded and counted
+        const uint8_t* cw_arg = tmp.cw;
+        int cw_mode = 0;
+        if (per_frame_ref) {
+            if (src_mode == SCPD_SRC_RANDOM) {
+                payload_kernel<<<gblocks, 256, 0, sg>>>(wpf, first_frame + done, nb, payload_seed, tmp.mask, tmp.ref[b]);
+                polar_transform_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, sg>>>(wpf, n, nb, tmp.ref[b], tmp.ref[b]);
+            } else {
+                ref_cycle_kernel<<<gblocks, 256, 0, sg>>>(wpf, first_frame + done, nb, tmp.cws, ncw, tmp.ref[b]);
+            }
+            CUDA_TRY(cudaGetLastError());
+            cw_arg = reinterpret_cast<const uint8_t*>(tmp.ref[b]);
+            cw_mode = 2;
+            d->launches += src_mode == SCPD_SRC_RANDOM ? 2 : 1;
+        }
+        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, cw_arg, cw_mode, d->d_llr2[b], sg);
         if (rc) break;
         CUDA_TRY(cudaEventRecord(d->ev_in[b], sg));
         CUDA_TRY(cudaStreamWaitEvent(sd, d->ev_in[b], 0));
         rc = scpd_decode(d, d->d_llr2[b], nb, d->d_xhat2[b], sd);
         if (rc) break;
-        CUDA_TRY(cudaEventRecord(d->ev_dec[b], sd));
-        rc = scpd_count_errors(n, nb, d->d_xhat2[b], tmp.ref, 0, (uint64_t*)d->d_counters, sd);
-        d->launches += 2;
+        const uint32_t* ref = per_frame_ref ? tmp.ref[b] : tmp.cws;  // nullptr = all-zero
+        rc = scpd_count_errors(n, nb, d->d_xhat2[b], ref, per_frame_ref ? 1 : 0, (uint64_t*)tmp.cnt, sd);
+        if (rc) break;
+        // information bits: (x^ ^ x) F^(x)n on the information positions
+        const unsigned long long total = (unsigned long long)nb * wpf;
+        if (ref && per_frame_ref) {
+            xor_words_kernel<<<gblocks, 256, 0, sd>>>(total, d->d_xhat2[b], ref, tmp.diff);
+        } else if (ref) {  // one shared codeword: x^ ^ x row by row through the cycle kernel's indexing
+            ref_cycle_kernel<<<gblocks, 256, 0, sd>>>(wpf, 0, nb, ref, 1, tmp.diff);
+            xor_words_kernel<<<gblocks, 256, 0, sd>>>(total, d->d_xhat2[b], tmp.diff, tmp.diff);
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(tmp.diff, d->d_xhat2[b], total * 4, cudaMemcpyDeviceToDevice, sd));
+        }
+        polar_transform_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, sd>>>(wpf, n, nb, tmp.diff, tmp.diff);
+        count_info_kernel<<<(unsigned)std::min<unsigned long long>((nb + 7) / 8, (unsigned long long)d->num_sms * 8), 256, 0, sd>>>(
+            wpf, d->cfg.k, nb, tmp.diff, tmp.mask, tmp.cnt + 6);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(d->ev_out[b], sd));
+        d->launches += 5;
     }
     cudaError_t e1 = cudaStreamSynchronize(sg), e2 = cudaStreamSynchronize(sd);  // also on the error paths: nothing in flight
     if (rc) return rc;
     if (e1 != cudaSuccess) return cuda_fail(e1, "generator stream");
     if (e2 != cudaSuccess) return cuda_fail(e2, "decode stream");
-    CUDA_TRY(cudaMemcpy(h_counters, d->d_counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h_counters, tmp.cnt, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SCPD_OK;
+}
+
+// sc_top_module of src/testbench with one stored codeword (or the all-zero one): the six counters of sc_error_counter
+extern "C" int scpd_run_ber(scpd_decoder* d, float ebn0_db, float rate, uint64_t first_frame, uint64_t nframes,
+                            uint8_t seed, const uint8_t* h_codeword, uint64_t h_counters[6]) {
+    if (!d || !h_counters) return set_error(SCPD_E_ARG, "scpd_run_ber: null argument");
+    uint64_t c[10];
+    const int rc = scpd_run_ber_ex(d, ebn0_db, rate, first_frame, nframes, seed, SCPD_SRC_CODEWORDS, h_codeword,
+                                   h_codeword ? 1u : 0u, 0, c);
+    if (rc) return rc;
+    std::memcpy(h_counters, c, 6 * sizeof(uint64_t));
     return SCPD_OK;
 }
 

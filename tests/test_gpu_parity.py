@@ -374,6 +374,23 @@ def test_slot_sliced_is_the_default_for_large_batches(scpd):
     assert "slot-sliced" in seen[32768] and "int16x2" in seen[2048], seen
 
 
+def test_validate_llr_counts_contract_violations(scpd):
+    import torch
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    rng = np.random.default_rng(9)
+    llr = rng.integers(-31, 32, size=(77, n)).astype(np.int8)
+    llr[3, 5] = 100
+    llr[70, 1000] = -128
+    llr[76, 1023] = -32
+    for q, want in ((8, 1), (6, 3), (7, 2)):
+        dec = scpd.Decoder(n, k, flags, llr_bits=q)
+        t = torch.from_numpy(llr).cuda()
+        assert dec.validate_llr(t) == want, q
+        assert dec.validate_llr(t.flatten()[1:n * 76 + 1].view(76, n)) in (want, want - 1)  # mis-aligned view
+        dec.close()
+
+
 def test_ragged_and_empty_batches(scpd):
     name, n, k, snr = CONFIG_SETS["c1"]
     flags = scpd.packed_flags(name, n)
@@ -437,6 +454,68 @@ def test_run_ber_counts(scpd):
     want = ol.count_errors(n, ol.decode(n, 16, 8, 0, 1, flags, llr), cw)
     assert cnt == want
     assert cnt[3] == nfr and cnt[2] == nfr * n and 0 < cnt[1] < nfr // 10
+
+
+def test_run_ber_ex_codeword_cycle_and_random_payload(scpd):
+    """scpd_run_ber_ex against the same chain taken apart: (i) the reference's encoder for N = 1024 -- its three stored
+    codewords in turn (sc_encoder.h:91-113) --, (ii) random information words encoded on the device.  Codeword-bit
+    counters as the reference counts them and information-bit counters, against generate(device) -> oracle decode ->
+    host counts; batches start at an odd stream position."""
+    import torch
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    cws = ol.golden_codewords()["cw1024x512"]
+    dec = scpd.Decoder(n, k, flags)
+    nfr, first = 3000, 77
+
+    def host_counts(x):  # x: uint8 [nfr, n] codewords actually sent
+        llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n), first_frame=first, codeword=x).cpu().numpy()
+        xhat = ol.decode(n, 16, 8, 0, 1, flags, llr)
+        want = ol.count_errors(n, xhat, x)
+        du = ol.polar_transform(xhat ^ x)[:, flags == 1]
+        e = du.sum(axis=1)
+        return want + [int(e.sum()), int((e != 0).sum()), nfr * k, nfr]
+
+    sent = cws[(first + np.arange(nfr)) % 3]
+    got = dec.run_ber_ex(snr, k / n, nfr, first_frame=first, codewords=cws)
+    assert got == host_counts(sent)
+    assert 0 < got[1] < nfr // 10 and 0 < got[7] <= got[1]
+    # one stored codeword and the all-zero codeword through the same entry point
+    assert dec.run_ber_ex(snr, k / n, nfr, first_frame=first, codewords=cws[1])[:6] == dec.run_ber(snr, k / n, nfr, first_frame=first, codeword=cws[1])
+    assert dec.run_ber_ex(snr, k / n, nfr, first_frame=first)[:6] == dec.run_ber(snr, k / n, nfr, first_frame=first)
+    # random payloads: restate the source on the host, encode with the oracle's transform
+    u = ol.unpack_bits(scpd.payload_words(5, first, nfr, flags), n)
+    assert (u[:, flags == 0] == 0).all() and 0.45 < u[:, flags == 1].mean() < 0.55
+    x = ol.polar_transform(u)
+    got = dec.run_ber_ex(snr, k / n, nfr, first_frame=first, random_payload=True, payload_seed=5)
+    assert got == host_counts(x)
+    dec.close()
+
+
+def test_stage_time_matrix(scpd):
+    """scpd_stage_time: measured cycles per function x level.  Visits must equal the schedule's op counts
+    times the number of profiled warps; cycles must be positive exactly where there are visits; the 64-LLR nodes (row R)
+    and the f / g rows carry most of the time."""
+    import torch
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags)
+    llr = scpd.channel_generate(n, 148 * 16 * 32, scpd.sigma(snr, k / n))
+    dec.stage_timing(True)
+    dec.decode(llr)
+    torch.cuda.synchronize()
+    cyc, vis = dec.stage_time()
+    assert "slot-sliced" in dec.last_kernel_name
+    assert ((cyc > 0) == (vis > 0)).all()
+    warps = int(vis[scpd.STAGE_FUNCS.index("H"), 10])  # one H at the root per profiled warp and task
+    assert warps >= 1 and vis[scpd.STAGE_FUNCS.index("R"), 6] == 15 * warps  # 15 nodes of 64 LLRs are decoded (c1, R0+R1)
+    assert vis[scpd.STAGE_FUNCS.index("F"), 10] == warps and vis[scpd.STAGE_FUNCS.index("G"), 10] == warps
+    share = cyc.sum(axis=1) / cyc.sum()
+    assert share[scpd.STAGE_FUNCS.index("R")] > 0.3 and share[scpd.STAGE_FUNCS.index("G")] > share[scpd.STAGE_FUNCS.index("H")]
+    cyc2, vis2 = dec.stage_time()
+    assert cyc2.sum() == 0 and vis2.sum() == 0  # read clears
+    dec.stage_timing(False)
+    dec.close()
 
 
 def test_extract_info_and_roundtrip_full_size(scpd):
