@@ -502,7 +502,7 @@ uint32_t ss_sub32(uint32_t s, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3
 }
 
 // One lane's view of the decoder state.  All pointers already include the lane.
-template <int Q, int LOG2PAR, bool EXT>
+template <int Q, int LOG2PAR, bool EXT, bool PROF = false>
 struct SsThread {
     static constexpr int P = Q - 1;
     static constexpr int FMT = bs::FMT_CA2;
@@ -796,7 +796,7 @@ struct SsThread {
 #if defined(__CUDA_ARCH__)
             // measured counterpart of the reference's function x level monitor (sc_monitor.h:50-441): cycles between
             // the fetch of this op and the fetch of the next, for one warp per CTA
-            if (prof_on) {
+            if (PROF && prof_on) {
                 const long long now = clock64();
                 if (prof_fn < 6u && (threadIdx.x & 31u) == 0u) {
                     atomicAdd(p.prof + prof_fn * 32u + prof_l, (unsigned long long)(now - prof_t0));
@@ -899,11 +899,12 @@ __global__ void __launch_bounds__(256) ss_planes_kernel(const int8_t* __restrict
 #ifndef SCPD_SS_THREADS
 #define SCPD_SS_THREADS 512  // upper bound of the CTA size: 16 warps, one CTA per SM, up to 128 registers
 #endif
-template <int Q, int LOG2PAR, bool EXT>
+// PROF: the build with the per-stage clock64() histogram (scpd_stage_timing); the production kernel carries none of it
+template <int Q, int LOG2PAR, bool EXT, bool PROF = false>
 __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const SsParams p) {
     extern __shared__ __align__(16) uint4 ss_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    SsThread<Q, LOG2PAR, EXT> t(p);
+    SsThread<Q, LOG2PAR, EXT, PROF> t(p);
     t.sm = ss_smem + (size_t)warp * p.sm_stride + lane;
     uint32_t* sm_sched = reinterpret_cast<uint32_t*>(ss_smem + (size_t)nwarps * p.sm_stride);
     // tensor memory for the alpha level p.ltm: warp w owns lanes 32 (w % 4) .. +31 (the only ones it can reach) and the
@@ -934,7 +935,7 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     } else {
         t.sched = p.sched;
     }
-    t.prof_on = p.prof != nullptr && warp == 0;
+    t.prof_on = PROF && p.prof != nullptr && warp == 0;
     const unsigned long long slot_id = (unsigned long long)blockIdx.x * nwarps + warp;
     t.wsl = p.ws + slot_id * p.ws_stride + lane;
     for (unsigned long long task = slot_id; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {

@@ -290,9 +290,11 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
 
 typedef void (*ss_kernel_t)(const SsParams);
 // Instantiated (LLR_BITS, log2 PAR, EXTENDED) combinations of the slot-sliced kernel (CA2 only).
-static ss_kernel_t ss_kernel_ptr(int q, int log2par, int ext) {
+// prof: the instrumented build (scpd_stage_timing), instantiated for the BASELINE setting only
+static ss_kernel_t ss_kernel_ptr(int q, int log2par, int ext, bool prof = false) {
+    if (prof) return (q == 8 && log2par == 4 && ext == 1) ? sc_decode_ss_kernel<8, 4, true, true> : nullptr;
 #define SS_K(Q, LP, E) \
-    if (q == Q && log2par == LP && ext == (E ? 1 : 0)) return sc_decode_ss_kernel<Q, LP, E>;
+    if (q == Q && log2par == LP && ext == (E ? 1 : 0)) return sc_decode_ss_kernel<Q, LP, E, false>;
     SS_K(8, 4, true)
 #ifndef SCPD_FAST_BUILD
     SS_K(8, 4, false)
@@ -874,7 +876,7 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     for (int l = 0; l < 24; l++) p.aoff[l] = d->ss_plan.aoff[l];
     p.prof = d->d_ss_prof;
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
-    ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended);
+    ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->d_ss_prof != nullptr);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(warps * 32)), smem, st>>>(p);
     snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_ss_kernel (slot-sliced, lane per frame, %d warps/CTA)", warps);
@@ -1125,8 +1127,11 @@ extern "C" int scpd_extract_info(scpd_decoder* d, const uint32_t* d_xhat, size_t
 // SM-clock cycles it spends in each schedule op to a [function][level] histogram.
 extern "C" int scpd_stage_timing(scpd_decoder* d, int enable) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_stage_timing: null decoder");
-    if (!d->ss_ok) return set_error(SCPD_E_UNSUPPORTED, "scpd_stage_timing: only the slot-sliced kernel measures per-stage time");
+    ss_kernel_t kp = d->ss_ok ? ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, true) : nullptr;
+    if (!kp)
+        return set_error(SCPD_E_UNSUPPORTED, "scpd_stage_timing: the instrumented slot-sliced kernel exists for CA2, LLR_BITS 8, PAR 16, EXTENDED only");
     CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
     if (enable && !d->d_ss_prof) {
         CUDA_TRY(cudaMalloc(&d->d_ss_prof, 2 * 6 * 32 * sizeof(unsigned long long)));
