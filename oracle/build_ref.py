@@ -51,6 +51,16 @@ CONFIGS = [
     # NOT the plain-SC contract of this library; built to measure how far the reference's own pruning departs from it
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 6, "sm", 1, 2),
     (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 8, "ca2", 1, 2),
+    # more PRUNING_LEVEL 2 builds: they pin sco_decode_l2 (the restatement of that decoder) over PAR / Q / format / N
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 4, 8, "ca2", 1, 2),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 64, 8, "ca2", 1, 2),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 16, 8, "ca2", 0, 2),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 64, 7, "sm", 1, 2),
+    (1024, 512, "Frozen_Bit_Tab/FB_N1024_K512.txt", 0, 4, 9, "sm", 1, 2),
+    (512, 256, "Frozen_Bit_Tab/FB_N512_K256.txt", 0, 16, 8, "ca2", 1, 2),
+    (8, 4, "Frozen_Bit_Tab/FB_N8_K4.txt", 0, 2, 8, "ca2", 1, 2),
+    (4096, 3072, "Generated_Frozen_Bit/frozen_n_4096_k_3072.txt", 1, 16, 8, "ca2", 1, 2),
+    (32768, 29492, "Generated_Frozen_Bit/frozen_n_32768_k_29492_snr_4_5.txt", 1, 16, 8, "ca2", 1, 2),
     # BASELINE configs 2..5 at the headline setting
     (4096, 3072, "Generated_Frozen_Bit/frozen_n_4096_k_3072.txt", 1, 16, 8, "ca2", 1),
     (32768, 29492, "Generated_Frozen_Bit/frozen_n_32768_k_29492_snr_4_5.txt", 1, 16, 8, "ca2", 1),

@@ -216,6 +216,139 @@ static void node_rec(const ctx_t* c, int n, int o, const uint32_t* alpha, uint8_
     for (int i = 0; i < h; i++) beta[i] ^= beta[h + i]; /* h_loop :903-932 */
 }
 
+/* ------------------------------------------------------------------ PRUNING_LEVEL 2 (REP / SPC shortcuts)
+ * Restatement of the reference built with PRUNING_LEVEL 2, ELAG_R1 = ELAG_REP = ELAG_SPC = ELAG_H0 = 1,
+ * ELAG_RARE = ELAG_REP2 = ELAG_SPC2 = 0 (src/module/config.h as checked in, PRUNING_LEVEL raised to 2).
+ * It is NOT plain SC: a repetition child decides on a saturating running sum, a single-parity-check child
+ * on signs + one flip.  Pinned on oracle/_ref/refdec_*_pl2.so (tests/test_oracle.py).                      */
+enum { T_R0 = 0x0, T_R1 = 0xF, T_REP = 0x2, T_SPC = 0x4, T_RN = 0x8 }; /* my_module.h NODE_* codes */
+
+/* do_prunning (my_module.h:61-166): the type of one PAR-wide word of the frozen table */
+static int l2_word_type(const uint8_t* fb, int p) {
+    int cnt = 0;
+    for (int i = 0; i < p; i++) cnt += fb[i] ? 1 : 0;
+    if (cnt == 0) return T_R0;
+    if (cnt == p) return T_R1;
+    if (cnt == 1 && fb[p - 1]) return T_REP;
+    if (cnt == p - 1 && !fb[0]) return T_SPC;
+    return T_RN;
+}
+/* F_STATE :337-545 / G_STATE: the child's type accumulated over its words */
+static int l2_type(const ctx_t* c, int o, int n) {
+    int p = c->par, m = n / p;
+    int all_or = 0, all_and = 0xF, rep_or = 0, spc_and = 0xF, first = 0, last = 0;
+    for (int k = 0; k < m; k++) {
+        int t = l2_word_type(c->flags + o + k * p, p);
+        all_or |= t;
+        all_and &= t;
+        if (k < m - 1) rep_or |= t;
+        if (k > 0) spc_and &= t;
+        if (k == 0) first = t;
+        last = t;
+    }
+    if (all_or == 0) return T_R0;
+    if (all_and == 0xF) return T_R1;
+    if (rep_or == 0 && (last >> 1) == 1) return T_REP;
+    if (spc_and == 0xF && (first >> 1) == 2) return T_SPC;
+    return T_RN;
+}
+/* ADDER_TREE_<PAR> (functions.h:3141-3260): sum of one word plus the running sum, at width q + log2(par) + 1 */
+static uint32_t l2_adder_tree(const ctx_t* c, const uint32_t* word, uint32_t old_sum) {
+    int p = c->par, lg = 0;
+    while ((1 << lg) < p) lg++;
+    int wsum = c->q + lg + 1;
+    if (c->format == SCO_CA2) { /* ADD_TREE_*_CA2 :2925-3030 is exact, then qadd (saturating) with old_sum */
+        int64_t t = 0;
+        for (int i = 0; i < p; i++) t += sx(word[i], c->q);
+        return c2_sat(wsum, t + sx(old_sum, wsum));
+    }
+    /* ADD_TREE_*_SM :3032-3140: halves folded with qfull_adder_sm, one more bit per stage */
+    uint32_t v[512];
+    int w = c->q;
+    for (int i = 0; i < p; i++) v[i] = word[i];
+    for (int h = p / 2; h >= 1; h /= 2, w++)
+        for (int i = 0; i < h; i++) v[i] = sm_addsub(w, v[i], v[i + h], 0);
+    /* v[0]: w = q + lg bits (sign + magnitude); extended by one magnitude bit, then qfull_adder_sat_sm<wsum> */
+    uint32_t ext = (((v[0] >> (w - 1)) & 1u) << (wsum - 1)) | (v[0] & mask_w(w - 1));
+    uint32_t s = sm_addsub(wsum, ext, old_sum, 0);                        /* (sign, wsum-bit sum) */
+    uint32_t sat = sm_sat(wsum - 1, s & mask_w(wsum));                    /* qsat_sm<wsum-1> */
+    return (((s >> wsum) & 1u) << (wsum - 1)) | sat;
+}
+/* Min_Mask_TREE_<PAR> (functions.h:3450-3973): tournament over halves, the upper element wins only when
+ * strictly smaller; returns the minimum magnitude and the one-hot position */
+static void l2_min_mask(const ctx_t* c, const uint32_t* word, uint32_t* minv, int* pos) {
+    int p = c->par;
+    uint32_t v[512];
+    int idx[512];
+    for (int i = 0; i < p; i++) {
+        v[i] = (c->format == SCO_CA2) ? c2_abs(c->q, word[i]) : sm_mag(c->q, word[i]);
+        idx[i] = i;
+    }
+    for (int h = p / 2; h >= 1; h /= 2)
+        for (int i = 0; i < h; i++) {
+            int up = (c->format == SCO_CA2) ? (sx(v[i + h], c->q) < sx(v[i], c->q)) : (v[i + h] < v[i]);
+            if (up) {
+                v[i] = v[i + h];
+                idx[i] = idx[i + h];
+            }
+        }
+    *minv = v[0] & mask_w(c->q);
+    *pos = idx[0];
+}
+
+static void l2_rec(const ctx_t* c, int n, int o, const uint32_t* alpha, uint8_t* beta, uint32_t* stack) {
+    if (n == c->par) { /* R_STATE: leaves keep Spec_Polar_Decoder at PRUNING_LEVEL 2 (library.h:170-198) */
+        leaf_rec(c, n, c->q, alpha, c->flags + o, beta, stack);
+        return;
+    }
+    int h = n / 2, p = c->par;
+    uint32_t* child = stack;
+    uint32_t* next = stack + h;
+    /* the root's own children are never shortcut (INIT :285-336 enters F_STATE / G_STATE directly) */
+    int tl = (n == c->n) ? T_RN : l2_type(c, o, h);
+    int tr_ = (n == c->n) ? T_RN : l2_type(c, o + h, h);
+    if (tl == T_R0) { /* left child skipped, H0 instead of H (my_module.h H0_STATE) */
+        memset(beta, 0, (size_t)h);
+    } else {
+        for (int i = 0; i < h; i++) child[i] = sco_f(c->format, c->q, alpha[i], alpha[h + i]);
+        if (tl == T_REP) { /* F_REP_STATE :1292-1390 */
+            uint32_t sum = 0;
+            int lg = 0;
+            while ((1 << lg) < p) lg++;
+            for (int k = 0; k < h / p; k++) sum = l2_adder_tree(c, child + k * p, sum);
+            memset(beta, sco_sign(c->q + lg + 1, sum), (size_t)h);
+        } else {
+            l2_rec(c, h, o, child, beta, next);
+        }
+    }
+    for (int i = 0; i < h; i++)
+        child[i] = sco_g(c->format, c->q, alpha[i], alpha[h + i], tl == T_R0 ? 0 : beta[i]);
+    if (tr_ == T_R1) { /* G_R1_STATE :1571-1642 */
+        for (int i = 0; i < h; i++) beta[h + i] = (uint8_t)sco_sign(c->q, child[i]);
+    } else if (tr_ == T_SPC) { /* G_SPC_STATE :1737-1842 */
+        int parity = 0, min_word = 0, min_pos = 0;
+        uint32_t old_min = mask_w(c->q);
+        for (int k = 0; k < h / p; k++) {
+            for (int i = 0; i < p; i++) {
+                beta[h + k * p + i] = (uint8_t)sco_sign(c->q, child[k * p + i]);
+                parity ^= beta[h + k * p + i];
+            }
+            uint32_t mv;
+            int pos;
+            l2_min_mask(c, child + k * p, &mv, &pos);
+            if (mv < old_min) {
+                old_min = mv;
+                min_word = k;
+                min_pos = pos;
+            }
+        }
+        if (parity) beta[h + min_word * p + min_pos] ^= 1;
+    } else {
+        l2_rec(c, h, o + h, child, beta + h, next);
+    }
+    for (int i = 0; i < h; i++) beta[i] ^= beta[h + i];
+}
+
 static int check_cfg(const sco_config* cfg) {
     if (!cfg) return -1;
     int n = cfg->n, p = cfg->par;
@@ -228,7 +361,7 @@ static int check_cfg(const sco_config* cfg) {
 }
 
 static int decode_impl(const sco_config* cfg, const uint8_t* flags, const int8_t* llr, size_t nframes,
-                       uint8_t* xhat, uint32_t* xhat32, sco_stats* st) {
+                       uint8_t* xhat, uint32_t* xhat32, sco_stats* st, int level2) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     int n = cfg->n;
@@ -250,7 +383,8 @@ static int decode_impl(const sco_config* cfg, const uint8_t* flags, const int8_t
     for (size_t f = 0; f < nframes; f++) {
         const int8_t* in = llr + f * (size_t)n;
         for (int i = 0; i < n; i++) alpha[i] = sco_input(cfg->format, cfg->llr_bits, in[i]); /* wrapper_in.h:33-34 */
-        node_rec(&c, n, 0, alpha, beta, alpha + n);
+        if (level2) l2_rec(&c, n, 0, alpha, beta, alpha + n);
+        else node_rec(&c, n, 0, alpha, beta, alpha + n);
         if (xhat) memcpy(xhat + f * (size_t)n, beta, (size_t)n);
         if (xhat32) {
             if (n >= 32) {
@@ -275,15 +409,23 @@ static int decode_impl(const sco_config* cfg, const uint8_t* flags, const int8_t
 
 int sco_decode(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr, size_t nframes,
                uint8_t* xhat) {
-    return decode_impl(cfg, info_flags, llr, nframes, xhat, NULL, NULL);
+    return decode_impl(cfg, info_flags, llr, nframes, xhat, NULL, NULL, 0);
 }
 int sco_decode_packed(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr, size_t nframes,
                       uint32_t* xhat32) {
-    return decode_impl(cfg, info_flags, llr, nframes, NULL, xhat32, NULL);
+    return decode_impl(cfg, info_flags, llr, nframes, NULL, xhat32, NULL, 0);
 }
 int sco_decode_stats(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr, size_t nframes,
                      uint8_t* xhat, sco_stats* st) {
-    return decode_impl(cfg, info_flags, llr, nframes, xhat, NULL, st);
+    return decode_impl(cfg, info_flags, llr, nframes, xhat, NULL, st, 0);
+}
+int sco_decode_l2(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr, size_t nframes,
+                  uint8_t* xhat) {
+    return decode_impl(cfg, info_flags, llr, nframes, xhat, NULL, NULL, 1);
+}
+int sco_decode_l2_packed(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr, size_t nframes,
+                         uint32_t* xhat32) {
+    return decode_impl(cfg, info_flags, llr, nframes, NULL, xhat32, NULL, 1);
 }
 
 typedef struct {
@@ -296,7 +438,7 @@ typedef struct {
 } mt_job;
 static void* mt_run(void* p) {
     mt_job* j = (mt_job*)p;
-    j->rc = decode_impl(j->cfg, j->flags, j->llr, j->nframes, NULL, j->out, NULL);
+    j->rc = decode_impl(j->cfg, j->flags, j->llr, j->nframes, NULL, j->out, NULL, 0);
     return NULL;
 }
 int sco_decode_packed_mt(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr,

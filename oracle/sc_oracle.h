@@ -65,6 +65,13 @@ int sco_decode_packed(const sco_config* cfg, const uint8_t* info_flags, const in
 int sco_decode_packed_mt(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr,
                          size_t nframes, uint32_t* xhat32, int nthreads);
 
+/* The reference built with PRUNING_LEVEL 2 (REP / SPC / R1 / R0 shortcuts above the leaf word; config.h flags
+ * ELAG_R1 = ELAG_REP = ELAG_SPC = ELAG_H0 = 1, the rest 0).  Not plain SC: see sc_oracle.c. */
+int sco_decode_l2(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr,
+                  size_t nframes, uint8_t* xhat);
+int sco_decode_l2_packed(const sco_config* cfg, const uint8_t* info_flags, const int8_t* llr,
+                         size_t nframes, uint32_t* xhat32);
+
 /* Instrumentation for design studies (tests only): for each maximal all-information subtree,
  * counts visits and visits whose input LLRs contain a zero.  sizes indexed by log2(node size). */
 typedef struct {

@@ -60,6 +60,17 @@ def decode(n, par, q, fmt, ext, flags, llr):
     return out
 
 
+def decode_l2(n, par, q, fmt, ext, flags, llr):
+    """Oracle restatement of the reference built with PRUNING_LEVEL 2 (REP / SPC shortcuts): NOT plain SC."""
+    llr = np.ascontiguousarray(llr, np.int8)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    out = np.zeros(llr.shape, np.uint8)
+    cfg = OCfg(n, par, q, fmt, ext)
+    rc = lib().sco_decode_l2(ctypes.byref(cfg), P(flags), P(llr), ctypes.c_size_t(llr.shape[0]), P(out))
+    assert rc == 0, rc
+    return out
+
+
 def decode_packed(n, par, q, fmt, ext, flags, llr, threads=1):
     llr = np.ascontiguousarray(llr, np.int8)
     flags = np.ascontiguousarray(flags, np.uint8)

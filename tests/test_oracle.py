@@ -167,3 +167,46 @@ def test_reference_full_pruning_is_not_plain_sc(tag, q, fmt):
     noisy = ol.channel(n, 200, ol.sigma(1.0, k / n))
     differ = (ol.ref_decode(R, flags, noisy) != ol.decode(n, 16, q, fmt, 1, flags, noisy)).any(axis=1)
     assert 0 < differ.sum() < len(noisy)
+
+
+L2_BUILDS = [  # (oracle/_ref tag, n, k, table, PAR, Q, format, EXTENDED)
+    ("n1024_p16_q8_ca2_e1_pl2", 1024, 512, "FB_N1024_K512", 16, 8, 0, 1),
+    ("n1024_p16_q6_sm_e1_pl2", 1024, 512, "FB_N1024_K512", 16, 6, 1, 1),
+    ("n1024_p4_q8_ca2_e1_pl2", 1024, 512, "FB_N1024_K512", 4, 8, 0, 1),
+    ("n1024_p64_q8_ca2_e1_pl2", 1024, 512, "FB_N1024_K512", 64, 8, 0, 1),
+    ("n1024_p16_q8_ca2_e0_pl2", 1024, 512, "FB_N1024_K512", 16, 8, 0, 0),
+    ("n1024_p64_q7_sm_e1_pl2", 1024, 512, "FB_N1024_K512", 64, 7, 1, 1),
+    ("n1024_p4_q9_sm_e1_pl2", 1024, 512, "FB_N1024_K512", 4, 9, 1, 1),
+    ("n512_p16_q8_ca2_e1_pl2", 512, 256, "FB_N512_K256", 16, 8, 0, 1),
+    ("n8_p2_q8_ca2_e1_pl2", 8, 4, "FB_N8_K4", 2, 8, 0, 1),
+    ("n4096_p16_q8_ca2_e1_pl2", 4096, 3072, "frozen_n_4096_k_3072", 16, 8, 0, 1),
+    ("n32768_p16_q8_ca2_e1_pl2", 32768, 29492, "frozen_n_32768_k_29492_snr_4_5", 16, 8, 0, 1),
+]
+
+
+@pytest.mark.parametrize("tag,n,k,tab,par,q,fmt,ext", L2_BUILDS, ids=[b[0] for b in L2_BUILDS])
+def test_level2_restatement_matches_reference_pruning_level_2(tag, n, k, tab, par, q, fmt, ext):
+    """sco_decode_l2 (REP / SPC / R1 / R0 shortcuts, my_module.h:1292-1842) against the reference's own sources built
+    with PRUNING_LEVEL 2: noisy channel frames, the whole quantiser alphabet, the whole Q-bit range, near-zero LLRs
+    (ties in the SPC minimum search, zero sums in REP) -- frames on which plain SC answers differently."""
+    R = ol.ref_lib(tag)
+    if R is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    flags = scpd.packed_flags(tab, n)
+    rng = np.random.default_rng(n + par + q)
+    nf = 64 if n <= 4096 else 6
+    m = min(2 ** (q - 1) - 1, 127)
+    inputs = {
+        "noisy": ol.channel(n, nf, ol.sigma(1.0 if k / n < 0.6 else 3.0, k / n)),
+        "alphabet": rng.integers(-31, 32, size=(nf, n)).astype(np.int8),
+        "full": rng.integers(-m, m + 1, size=(nf, n)).astype(np.int8),
+        "near_zero": rng.integers(-2, 3, size=(nf, n)).astype(np.int8),
+        "zeros": np.zeros((2, n), np.int8),
+    }
+    departs = 0
+    for name, llr in inputs.items():
+        want = ol.ref_decode(R, flags, llr)
+        assert (ol.decode_l2(n, par, q, fmt, ext, flags, llr) == want).all(), name
+        departs += int((ol.decode(n, par, q, fmt, ext, flags, llr) != want).any(axis=1).sum())
+    if n >= 512:
+        assert departs > 0  # the inputs do exercise the shortcuts: plain SC disagrees on some of them
