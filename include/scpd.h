@@ -48,13 +48,20 @@ typedef enum {
 
 typedef enum { SCPD_FMT_CA2 = 0, SCPD_FMT_SIGMAG = 1 } scpd_format; /* config.h:11 CA2 / SIGMAG */
 
-/* Pruning: which proven-bit-identical node shortcuts the schedule may use.  None of them changes
- * a single output bit w.r.t. plain SC (reference PRUNING_LEVEL 0); they only skip work. */
+/* Pruning.  Modes 0..2: which proven-bit-identical node shortcuts the schedule may use.  None of them changes
+ * a single output bit w.r.t. plain SC (reference PRUNING_LEVEL 0); they only skip work.
+ * Mode 3 is a DIFFERENT DECODER, opt-in: the reference as it is checked in (config.h:16-30: PRUNING_LEVEL 2 with
+ * ELAG_R1 / ELAG_REP / ELAG_SPC / ELAG_H0).  Above the PAR-wide leaf a child whose words are all-frozen but a last
+ * repetition word is decided by the sign of a saturating sum (my_module.h:1292-1390), an all-information child by the
+ * sign of g (:1571-1642), a child that is one single-parity-check word followed by all-information words by the
+ * signs of g with the least reliable one flipped on odd parity (:1737-1842).  Its output differs from plain SC on
+ * noisy frames (as the reference's own does, tests/test_oracle.py); it is bit-exact with the reference built that way. */
 typedef enum {
-    SCPD_PRUNE_NONE = 0, /* visit every node, as PRUNING_LEVEL 0 (config.h:16) */
-    SCPD_PRUNE_R0 = 1,   /* skip all-frozen subtrees */
-    SCPD_PRUNE_R0_R1 = 2 /* + all-information subtrees by hard decision when no input LLR is a
-                            CA2 zero (falls back to plain SC on that node otherwise) */
+    SCPD_PRUNE_NONE = 0,  /* visit every node, as PRUNING_LEVEL 0 (config.h:16) */
+    SCPD_PRUNE_R0 = 1,    /* skip all-frozen subtrees */
+    SCPD_PRUNE_R0_R1 = 2, /* + all-information subtrees by hard decision when no input LLR is a
+                             CA2 zero (falls back to plain SC on that node otherwise) */
+    SCPD_PRUNE_REF_LEVEL2 = 3 /* the reference's PRUNING_LEVEL 2 decoder (R0 / R1 / REP / SPC / H0); par 2..256 */
 } scpd_pruning;
 
 /* Replaces the compile-time macros of config.h:2-16 and polar_parameters.h:4-11. */
@@ -138,9 +145,11 @@ const char* scpd_last_kernel_name(const scpd_decoder* dec);
  * per frame and the trip counts of the reference's pipelined loops (f_loop / g_loop / h_loop,
  * my_module.h:373,704,903: half the node's PAR-wide words; one per leaf decode R, :592-595).  With
  * SCPD_PRUNE_NONE this is the reference at PRUNING_LEVEL 0 and total_iterations its loop cycles per frame;
- * with pruning it is the walk this library executes (R0 / R1: nodes skipped / decided by hard decision). */
+ * with pruning it is the walk this library executes (R0 / R1: nodes skipped / decided by hard decision); with
+ * SCPD_PRUNE_REF_LEVEL2 the reference FSM at PRUNING_LEVEL 2: F / G / H / R as above, R0 = children skipped (H0 path),
+ * R1 = G_R1_STATE, REP = F_REP_STATE, SPC = G_SPC_STATE (their loops run over the child's words). */
 enum { SCPD_STAGE_F = 0, SCPD_STAGE_G = 1, SCPD_STAGE_H = 2, SCPD_STAGE_R = 3, SCPD_STAGE_R0 = 4,
-       SCPD_STAGE_R1 = 5, SCPD_STAGE_FUNCS = 6 };
+       SCPD_STAGE_R1 = 5, SCPD_STAGE_REP = 6, SCPD_STAGE_SPC = 7, SCPD_STAGE_FUNCS = 8 };
 typedef struct {
     uint64_t visits[SCPD_STAGE_FUNCS][32];     /* [function][l]: node visits per frame            */
     uint64_t iterations[SCPD_STAGE_FUNCS][32]; /* [function][l]: loop iterations (PAR-wide words) */

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SCPD_LIB_PATH") or os.path.join(_HERE, "libscpd.so") 
 DATA_DIR = os.path.join(_HERE, "data")
 
 FMT_CA2, FMT_SIGMAG = 0, 1
-PRUNE_NONE, PRUNE_R0, PRUNE_R0_R1 = 0, 1, 2
+PRUNE_NONE, PRUNE_R0, PRUNE_R0_R1, PRUNE_REF_LEVEL2 = 0, 1, 2, 3
 OK, E_ARG, E_CONFIG, E_UNSUPPORTED, E_IO, E_CUDA, E_NOMEM = range(7)
 
 
@@ -28,11 +28,11 @@ class Config(ctypes.Structure):
 
 class StageMatrix(ctypes.Structure):
     """scpd_stage_matrix: [function][level] node visits and loop iterations per frame."""
-    _fields_ = [("visits", (ctypes.c_uint64 * 32) * 6), ("iterations", (ctypes.c_uint64 * 32) * 6),
+    _fields_ = [("visits", (ctypes.c_uint64 * 32) * 8), ("iterations", (ctypes.c_uint64 * 32) * 8),
                 ("total_iterations", ctypes.c_uint64)]
 
 
-STAGE_FUNCS = ("F", "G", "H", "R", "R0", "R1")
+STAGE_FUNCS = ("F", "G", "H", "R", "R0", "R1", "REP", "SPC")
 
 
 class ScpdError(RuntimeError):
@@ -151,12 +151,12 @@ def sigma(ebn0_db, rate):
 
 def stage_profile(n, k, flags, par=16, pruning=PRUNE_NONE):
     """The function x level matrix of the reference's sc_monitor (sc_monitor.h:50-441) from the frozen table:
-    returns (visits, iterations, total) with visits / iterations numpy [6, 32] indexed [STAGE_FUNCS, log2 node size]."""
+    returns (visits, iterations, total) with visits / iterations numpy [8, 32] indexed [STAGE_FUNCS, log2 node size]."""
     flags = np.ascontiguousarray(flags, np.uint8)
     cfg = Config(n, k, par, 8, FMT_CA2, 1, pruning, 0)
     m = StageMatrix()
     check(lib.scpd_stage_profile(ctypes.byref(cfg), _np_ptr(flags), ctypes.byref(m)))
-    return (np.array(m.visits, np.uint64).reshape(6, 32), np.array(m.iterations, np.uint64).reshape(6, 32),
+    return (np.array(m.visits, np.uint64).reshape(8, 32), np.array(m.iterations, np.uint64).reshape(8, 32),
             int(m.total_iterations))
 
 

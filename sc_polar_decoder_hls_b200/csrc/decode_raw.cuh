@@ -12,6 +12,12 @@
 // schedule.h).  Only all-frozen nodes are pruned here (always identical: every decision of the
 // subtree is "& 0"); the rate-1 shortcut is not used because its proof needs in-range inputs.
 //
+// It is also the kernel of the reference-pruning mode (SCPD_PRUNE_REF_LEVEL2): the decoder the reference
+// is when built with its checked-in PRUNING_LEVEL 2 -- repetition children decided by the sign of a
+// saturating sum (OP_REP), all-information children by the sign of g (OP_GR1), single-parity-check
+// children by the signs of g with the least reliable one flipped on odd parity (OP_GSPC).  That decoder
+// is not plain SC; tests pin it on the reference's own sources built that way (oracle/_ref/*_pl2.so).
+//
 // Arithmetic contract (reference):
 //   CA2     f  F_function_C2  functions.h:48-61     qabs/qmin/qsign  scalar.h:9-36
 //           g  G_function_C2  functions.h:63-75     qsat             scalar.h:15-21
@@ -37,6 +43,7 @@ struct RawParams {
     uint32_t n, log2n, wpf;
     uint32_t q;        // LLR_BITS
     uint32_t sigmag;   // 0 = CA2, 1 = SIGMAG
+    uint32_t log2par;  // PAR-wide words (reference-pruning mode: word sums, minimum search order)
     uint32_t ls;             // alpha levels 0..ls in shared memory, ls+1..log2n-1 in the workspace
     uint32_t beta_in_smem;   // partial sums in shared memory (else workspace)
     uint32_t sm_words_per_frame;
@@ -172,6 +179,114 @@ struct RawDecoder {
         }
         __syncwarp();
     }
+    // ---- reference-pruning mode.  All three ops run on a node of 2^l LLRs above the leaf (l > log2par, width q) and use
+    // alpha[l-1] as scratch, as the f / g loops they replace would.
+    // beta[o..o+h) = sign bits of scratch[0..h)
+    __device__ void pack_signs(const uint32_t* v, uint32_t o, uint32_t h, int w) {
+        if (h >= 32) {
+            for (uint32_t wd = gl; wd < (h >> 5); wd += G) {
+                uint32_t bits = 0;
+                for (uint32_t b = 0; b < 32; b++) bits |= raw::sgn(v[32 * wd + b], w) << b;
+                beta[(o >> 5) + wd] = bits;
+            }
+        } else if (gl == 0) {
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < h; b++) bits |= raw::sgn(v[b], w) << b;
+            const uint32_t wd = o >> 5, sh = o & 31u;
+            beta[wd] = (beta[wd] & ~(((1u << h) - 1u) << sh)) | (bits << sh);
+        }
+    }
+    // F_REP_STATE my_module.h:1292-1390: sum = ADD_TREE_FUNCTION(f word, sum) over the words of the left child, all its
+    // bits = sign(sum).  ADDER_TREE_<PAR> (functions.h:3141-3260): the word folded by halves (exact; in SIGMAG with
+    // qfull_adder_sm, whose zero keeps a sign), then one saturating addition at width q + log2par + 1.
+    __device__ void op_rep(int l, uint32_t o) {
+        const uint32_t h = 1u << (l - 1);
+        const int w = width(l), lp = (int)p.log2par;
+        uint32_t* v = alpha(l - 1);
+        for (uint32_t i = gl; i < h; i += G) {
+            const uint32_t a = ld(l, i), b = ld(l, i + h);
+            v[i] = sm ? raw::f_sm(a, b, w) : (uint32_t)raw::val(raw::f_c2(a, b, w), w);
+        }
+        __syncwarp();
+        const uint32_t nwords = h >> lp;
+        for (int s = 0; s < lp; s++) {  // stage s: element i += element i + hh of every word, one bit wider
+            const uint32_t hh = (1u << lp) >> (s + 1);
+            for (uint32_t t = gl; t < nwords * hh; t += G) {
+                const uint32_t at = ((t / hh) << lp) + (t % hh);
+                v[at] = sm ? raw::addsub_sm(v[at], v[at + hh], 0u, w + s) : (uint32_t)((int)v[at] + (int)v[at + hh]);
+            }
+            __syncwarp();
+        }
+        const int wt = w + lp, ws = w + lp + 1;  // word sum: wt bits; running sum: ws bits
+        uint32_t bit = 0;
+        if (gl == 0) {
+            uint32_t sum = 0;
+            for (uint32_t k = 0; k < nwords; k++) {
+                const uint32_t t = v[k << lp];
+                if (sm) {  // qfull_adder_sat_sm<ws>(word sum extended by one magnitude bit, sum)   scalar.h:165-194
+                    const uint32_t ext = (raw::sgn(t, wt) << (ws - 1)) | (t & raw::mk(wt - 1));
+                    const uint32_t r = raw::addsub_sm(ext, sum, 0u, ws);
+                    const uint32_t mag = r & raw::mk(ws), top = raw::mk(ws - 2);
+                    sum = (((r >> ws) & 1u) << (ws - 1)) | (mag > top ? top : (mag & raw::mk(ws - 1)));
+                } else {  // qadd<ws>   scalar.h:49-54
+                    const int m = (1 << (ws - 1)) - 1;
+                    int x = raw::val(sum, ws) + (int)t;
+                    x = x > m ? m : (x < -m ? -m : x);
+                    sum = (uint32_t)x & raw::mk(ws);
+                }
+            }
+            bit = raw::sgn(sum, ws);
+        }
+        bit = __shfl_sync(0xFFFFFFFFu, bit, 0, G);
+        const uint32_t fill = bit ? 0xFFFFFFFFu : 0u;
+        if (h >= 32) {
+            for (uint32_t wd = gl; wd < (h >> 5); wd += G) beta[(o >> 5) + wd] = fill;
+        } else if (gl == 0) {
+            const uint32_t wd = o >> 5, lm = ((1u << h) - 1u) << (o & 31u);
+            beta[wd] = (beta[wd] & ~lm) | (fill & lm);
+        }
+        __syncwarp();
+    }
+    // G_R1_STATE :1571-1642 (spc = false) and G_SPC_STATE :1737-1842: right child = sign(g).  SPC: parity over the
+    // child; Min_Mask_TREE_<PAR> (functions.h:3450-3973) is a tournament over halves in which the upper element wins only
+    // when strictly smaller, and a later word replaces the minimum only when strictly smaller -- i.e. the minimum of
+    // (|g|, word, bit-reversed position in the word); that bit is flipped when the parity is odd.
+    __device__ void op_gsign(int l, uint32_t o, bool zero_beta, bool spc) {
+        const uint32_t h = 1u << (l - 1);
+        const int w = width(l), lp = (int)p.log2par;
+        uint32_t* v = alpha(l - 1);
+        uint32_t parity = 0, best = 0xFFFFFFFFu;
+        for (uint32_t i = gl; i < h; i += G) {
+            const uint32_t pos = o + i;
+            const uint32_t u = zero_beta ? 0u : (beta[pos >> 5] >> (pos & 31u)) & 1u;
+            const uint32_t a = ld(l, i), b = ld(l, i + h);
+            const uint32_t r = sm ? raw::g_sm(a, b, u, w, false) : raw::g_c2(a, b, u, w, false);
+            v[i] = r;
+            if (spc) {
+                parity ^= raw::sgn(r, w);
+                const uint32_t mag = sm ? (r & raw::mk(w - 1)) : raw::abs_c2(r, w);
+                const uint32_t j = i & ((1u << lp) - 1u);
+                const uint32_t key = (mag << 20) | ((i >> lp) << lp) | (__brev(j) >> (32 - lp));
+                best = key < best ? key : best;
+            }
+        }
+        __syncwarp();
+        pack_signs(v, o + h, h, w);
+        if (spc) {
+            for (int m = G / 2; m >= 1; m >>= 1) {
+                parity ^= __shfl_xor_sync(0xFFFFFFFFu, parity, m, G);
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, best, m, G);
+                best = other < best ? other : best;
+            }
+            __syncwarp();
+            if (gl == 0 && parity) {
+                const uint32_t kj = best & 0xFFFFFu, j = __brev(kj & ((1u << lp) - 1u)) >> (32 - lp);
+                const uint32_t pos = o + h + ((kj >> lp) << lp) + j;
+                beta[pos >> 5] ^= 1u << (pos & 31u);
+            }
+        }
+        __syncwarp();
+    }
     __device__ void op_p2(uint32_t o, uint32_t lf) {
         if (gl == 0) {
             const int w = width(1);
@@ -216,6 +331,9 @@ struct RawDecoder {
                 case OP_R0: op_r0(l, o); break;
                 case OP_P2: op_p2(o, op_lf(w)); break;
                 case OP_P1: op_p1(o, op_lf(w)); break;
+                case OP_REP: op_rep(l, o); break;
+                case OP_GR1: op_gsign(l, o, op_nosat(w), false); break;
+                case OP_GSPC: op_gsign(l, o, op_nosat(w), true); break;
                 default: break;
             }
         }

@@ -17,10 +17,46 @@ struct Walker {
     uint32_t log2par, pruning;
     const uint32_t* psum;
     scpd_stage_matrix* m;
+    const uint8_t* flags;
     uint32_t count(uint32_t o, uint32_t n) const { return psum[o + n] - psum[o]; }
     void visit(int fn, int l, uint64_t iters) {
         m->visits[fn][l] += 1;
         m->iterations[fn][l] += iters;
+    }
+    // the reference FSM at PRUNING_LEVEL 2 (schedule.h emit_l2; my_module.h:337-545 child types)
+    enum { T_R0, T_R1, T_REP, T_SPC, T_RN };
+    int word_type(uint32_t o) const {
+        const uint32_t p = 1u << log2par, c = count(o, p);
+        return c == 0 ? T_R0 : c == p ? T_R1 : (c == 1 && flags[o + p - 1]) ? T_REP : (c == p - 1 && !flags[o]) ? T_SPC : T_RN;
+    }
+    int child_type(uint32_t o, uint32_t n) const {
+        const uint32_t p = 1u << log2par, c = count(o, n);
+        if (c == 0) return T_R0;
+        if (c == n) return T_R1;
+        if (count(o, n - p) == 0 && word_type(o + n - p) == T_REP) return T_REP;
+        if (count(o + p, n - p) == n - p && word_type(o) == T_SPC) return T_SPC;
+        return T_RN;
+    }
+    void walk_l2(int l, uint32_t o, int top) {
+        const uint32_t n = 1u << l;
+        if ((uint32_t)l <= log2par) return visit(SCPD_STAGE_R, l, 1);
+        const uint64_t words = n >> log2par;
+        const uint32_t h = n >> 1;
+        int tl = child_type(o, h), tr = child_type(o + h, h);
+        if (l == top) tl = tr = T_RN;  // INIT enters F_STATE / G_STATE whatever the children are
+        if (tl == T_R0) visit(SCPD_STAGE_R0, l - 1, 0);
+        else if (tl == T_REP) visit(SCPD_STAGE_REP, l, words >> 1);
+        else {
+            visit(SCPD_STAGE_F, l, words >> 1);
+            walk_l2(l - 1, o, top);
+        }
+        if (tr == T_R1) visit(SCPD_STAGE_R1, l, words >> 1);
+        else if (tr == T_SPC) visit(SCPD_STAGE_SPC, l, words >> 1);
+        else {  // ELAG_RARE = 0: an all-frozen right child is walked like any other
+            visit(SCPD_STAGE_G, l, words >> 1);
+            walk_l2(l - 1, o + h, top);
+        }
+        visit(SCPD_STAGE_H, l, words >> 1);
     }
     void walk(int l, uint32_t o) {
         const uint32_t n = 1u << l, c = count(o, n);
@@ -51,7 +87,7 @@ extern "C" int scpd_stage_profile(const scpd_config* cfg, const uint8_t* flags, 
     if (!cfg || !flags || !out) return SCPD_E_ARG;
     const uint32_t n = cfg->n, par = cfg->par;
     if (n < 2 || (n & (n - 1)) || n > (1u << 20) || par < 1 || (par & (par - 1)) || 2 * par > n ||
-        cfg->pruning > SCPD_PRUNE_R0_R1)
+        cfg->pruning > SCPD_PRUNE_REF_LEVEL2 || (cfg->pruning == SCPD_PRUNE_REF_LEVEL2 && (par < 2 || par > 256)))
         return SCPD_E_CONFIG;
     std::memset(out, 0, sizeof *out);
     std::vector<uint32_t> psum(n + 1, 0);
@@ -59,8 +95,9 @@ extern "C" int scpd_stage_profile(const scpd_config* cfg, const uint8_t* flags, 
     int log2n = 0, log2par = 0;
     while ((1u << log2n) < n) log2n++;
     while ((1u << log2par) < par) log2par++;
-    Walker w{(uint32_t)log2par, cfg->pruning, psum.data(), out};
-    w.walk(log2n, 0);
+    Walker w{(uint32_t)log2par, cfg->pruning, psum.data(), out, flags};
+    if (cfg->pruning == SCPD_PRUNE_REF_LEVEL2) w.walk_l2(log2n, 0, log2n);
+    else w.walk(log2n, 0);
     for (int f = 0; f < SCPD_STAGE_FUNCS; f++)
         for (int l = 0; l < 32; l++) out->total_iterations += out->iterations[f][l];
     return SCPD_OK;

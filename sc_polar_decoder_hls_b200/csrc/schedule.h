@@ -33,6 +33,11 @@ enum Op : uint32_t {
     OP_P2 = 8,     // two-bit terminal, Spec_P2 functions.h:367-384; leaf flags = (f0, f1)
     OP_P1 = 9,     // one-bit terminal, Spec_P1 functions.h:355-364; leaf flag bit0 = f
     OP_SUB = 10,   // register subtree of size 2^l (fast kernel); followed by its node-type words
+    // reference-pruning mode (SCPD_PRUNE_REF_LEVEL2; the reference built with PRUNING_LEVEL 2), node of size 2^l at o:
+    OP_REP = 11,   // left child is a repetition node: its bits = sign of the saturating sum of f   F_REP_STATE :1292-1390
+    OP_GR1 = 12,   // right child is all-information: its bits = sign of g (bit 9: beta = 0)         G_R1_STATE  :1571-1642
+    OP_GSPC = 13,  // right child is a single parity check: signs of g, least reliable one flipped
+                   // when the parity is odd (bit 9: beta = 0)                                       G_SPC_STATE :1737-1842
 };
 
 SCPD_HD static inline uint32_t op_make(uint32_t opc, uint32_t level, uint32_t offset, uint32_t nosat = 0,
@@ -51,6 +56,8 @@ struct ScheduleStats {
     uint64_t n_g = 0;   // g element updates per frame
     uint64_t n_r0 = 0;  // pruned all-frozen nodes
     uint64_t n_r1 = 0;  // pruned all-information nodes
+    uint64_t n_rep = 0; // repetition nodes decided by their sum (reference-pruning mode)
+    uint64_t n_spc = 0; // single-parity-check nodes decided by signs + one flip (reference-pruning mode)
 };
 
 struct ScheduleBuilder {
@@ -180,6 +187,74 @@ struct ScheduleBuilder {
         ops[at] = (uint32_t)(ops.size() - at - 1);
     }
 
+    // ---- reference-pruning mode: the reference's own PRUNING_LEVEL 2 (config.h:16-30 as checked in: R1, REP, SPC, H0).
+    // NOT plain SC (tests/test_oracle.py).  do_prunning (my_module.h:61-166) types every PAR-wide word of the frozen
+    // table; F_STATE / G_STATE (:337-545) accumulate the words of a child into its type:
+    enum NodeType { T_R0, T_R1, T_REP, T_SPC, T_RN };
+    NodeType word_type(uint32_t o) const {
+        const uint32_t p = 1u << log2par, c = count(o, p);
+        if (c == 0) return T_R0;
+        if (c == p) return T_R1;
+        if (c == 1 && flags[o + p - 1]) return T_REP;
+        if (c == p - 1 && !flags[o]) return T_SPC;
+        return T_RN;
+    }
+    NodeType child_type(uint32_t o, uint32_t n) const {  // n >= PAR
+        const uint32_t p = 1u << log2par, c = count(o, n);
+        if (c == 0) return T_R0;
+        if (c == n) return T_R1;
+        if (count(o, n - p) == 0 && word_type(o + n - p) == T_REP) return T_REP;        // R0 words, then one REP word
+        if (count(o + p, n - p) == n - p && word_type(o) == T_SPC) return T_SPC;        // one SPC word, then R1 words
+        return T_RN;
+    }
+    void emit_l2(int l, uint32_t o) {
+        if (l <= log2par) {  // the PAR-wide leaf stays Spec_Polar_Decoder (library.h:170-198); "& 0" pruning is value-neutral
+            const int keep = pruning;
+            pruning = 1;
+            emit(l, o);
+            pruning = keep;
+            return;
+        }
+        const uint32_t n = 1u << l, h = n >> 1;
+        if (count(o, n) == 0) {
+            ops.push_back(op_make(OP_R0, l, o));
+            st.n_r0++;
+            return;
+        }
+        // INIT (:285-336) enters F_STATE / G_STATE for the root's children whatever their type
+        const bool root = l == log2n;
+        NodeType tl = child_type(o, h), tr = child_type(o + h, h);
+        if (root && tl != T_R0) tl = T_RN;
+        if (root && tr != T_R0) tr = T_RN;
+        const uint32_t zb = tl == T_R0 ? 1u : 0u;  // H0: the left child is skipped, g runs on beta = 0
+        if (tl == T_REP) {
+            ops.push_back(op_make(OP_REP, l, o));
+            st.n_rep++;
+            st.n_f += h;
+        } else if (tl != T_R0) {
+            ops.push_back(op_make(OP_F, l, o));
+            st.n_f += h;
+            emit_l2(l - 1, o);
+        }
+        if (tr == T_R0) {
+            ops.push_back(op_make(OP_R0, l - 1, o + h));
+            st.n_r0++;
+        } else if (tr == T_R1) {
+            ops.push_back(op_make(OP_GR1, l, o, zb));
+            st.n_r1++;
+            st.n_g += h;
+        } else if (tr == T_SPC) {
+            ops.push_back(op_make(OP_GSPC, l, o, zb));
+            st.n_spc++;
+            st.n_g += h;
+        } else {
+            ops.push_back(op_make(zb ? OP_G0 : OP_G, l, o, nosat(l)));
+            st.n_g += h;
+            emit_l2(l - 1, o + h);
+        }
+        ops.push_back(op_make(zb ? OP_HCOPY : OP_H, l, o));
+    }
+
     void emit(int l, uint32_t o) {
         const uint32_t n = 1u << l;
         const uint32_t c = count(o, n);
@@ -257,7 +332,8 @@ static inline std::vector<uint32_t> build_schedule(int log2n, int log2par, int e
     const uint32_t n = 1u << log2n;
     b.psum.assign(n + 1, 0);
     for (uint32_t i = 0; i < n; i++) b.psum[i + 1] = b.psum[i] + (flags[i] ? 1u : 0u);
-    b.emit(log2n, 0);
+    if (pruning == 3) b.emit_l2(log2n, 0);  // SCPD_PRUNE_REF_LEVEL2 (raw-pattern kernel only)
+    else b.emit(log2n, 0);
     b.ops.push_back(op_make(OP_END, 0, 0));
     b.ops.push_back(op_make(OP_END, 0, 0));  // kernels prefetch one word ahead
     b.st.n_ops = b.ops.size();

@@ -499,8 +499,8 @@ static const void* raw_kernel_ptr(int group) {
 static int plan_raw(scpd_decoder* d, const uint8_t* flags) {
     d->raw_ok = false;
     // all-frozen nodes are pruned (identical for any input); the rate-1 shortcut is not (decode_raw.cuh)
-    d->raw_sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended,
-                                       std::min<int>((int)d->cfg.pruning, SCPD_PRUNE_R0), flags, &d->raw_stats);
+    const int raw_pruning = d->cfg.pruning == SCPD_PRUNE_REF_LEVEL2 ? 3 : std::min<int>((int)d->cfg.pruning, SCPD_PRUNE_R0);
+    d->raw_sched_host = build_schedule(d->log2n, d->log2par, (int)d->cfg.extended, raw_pruning, flags, &d->raw_stats);
     d->raw_group = d->log2n <= 7 ? 8 : 32;
     const int f_per_cta = d->warps_per_cta * (32 / d->raw_group);
     const size_t per_frame_words = 100 * 1024 / 4 / f_per_cta;  // two CTAs per SM
@@ -578,7 +578,9 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     if (k != cfg->k) return set_error(SCPD_E_CONFIG, "k differs from the number of information flags");
     if (cfg->format != SCPD_FMT_CA2 && cfg->format != SCPD_FMT_SIGMAG)
         return set_error(SCPD_E_CONFIG, "format must be SCPD_FMT_CA2 or SCPD_FMT_SIGMAG");
-    if (cfg->pruning > SCPD_PRUNE_R0_R1) return set_error(SCPD_E_CONFIG, "unknown pruning mode");
+    if (cfg->pruning > SCPD_PRUNE_REF_LEVEL2) return set_error(SCPD_E_CONFIG, "unknown pruning mode");
+    if (cfg->pruning == SCPD_PRUNE_REF_LEVEL2 && (par < 2 || par > 256))
+        return set_error(SCPD_E_CONFIG, "SCPD_PRUNE_REF_LEVEL2 needs par in 2..256 (ADD_TREE_FUNCTION, library.h:72-93)");
     if (cfg->extended > 1) return set_error(SCPD_E_CONFIG, "extended must be 0 or 1");
     if (cfg->llr_bits < 5 || cfg->llr_bits > 9)
         return set_error(SCPD_E_CONFIG, "llr_bits outside 5..9 (range swept by script/script_tests.sh)");
@@ -593,6 +595,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
         cfg->llr_bits < 6 || (cfg->extended && cfg->llr_bits + (uint32_t)log2par > 16) ||
         (cfg->format == SCPD_FMT_SIGMAG &&
          (!bs_kernel_ptr(SCPD_FMT_SIGMAG, (int)cfg->llr_bits, log2par, (int)cfg->extended, 0) || n < 128)) ||
+        cfg->pruning == SCPD_PRUNE_REF_LEVEL2 ||  // the reference's REP / SPC decoder: ops of decode_raw.cuh only
         (ksel_raw && std::strcmp(ksel_raw, "raw") == 0);
 
     cudaError_t e = cudaSetDevice(device);
@@ -605,7 +608,8 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     d->log2n = ilog2(n);
     d->log2par = log2par;
     d->wpf = n >= 32 ? n / 32 : 1;
-    d->sched_host = build_schedule(d->log2n, d->log2par, (int)cfg->extended, (int)cfg->pruning, flags, &d->stats);
+    d->sched_host = build_schedule(d->log2n, d->log2par, (int)cfg->extended,
+                                   std::min<int>((int)cfg->pruning, SCPD_PRUNE_R0_R1), flags, &d->stats);
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) {
@@ -906,6 +910,7 @@ static int decode_raw(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint
     p.wpf = d->wpf;
     p.q = d->cfg.llr_bits;
     p.sigmag = d->cfg.format == SCPD_FMT_SIGMAG ? 1u : 0u;
+    p.log2par = (uint32_t)d->log2par;
     p.ls = d->raw_ls;
     p.beta_in_smem = d->raw_beta_in_smem;
     p.sm_words_per_frame = d->raw_sm_words;

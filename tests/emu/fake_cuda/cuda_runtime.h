@@ -42,6 +42,11 @@ template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t __brev(uint32_t v) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cuda_emu::collective_sync(); }
 // CTA barrier over the fibers of run_cta (kernels whose warps are emulated one after the other through run_warp
 // see a CTA of one warp and must not rely on cross-warp state under emulation)

@@ -383,7 +383,8 @@ int emu_raw_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int ext
     if (g == 32) body = [](void* a) { sc_decode_raw_kernel<32>(static_cast<RL*>(a)->p); };
     if (!body) return -1;
     ScheduleStats st;
-    std::vector<uint32_t> sched = build_schedule(log2n, log2par, extended, pruning > 1 ? 1 : pruning, flags, &st);
+    // pruning 3 = SCPD_PRUNE_REF_LEVEL2 (REP / R1 / SPC ops); otherwise only all-frozen nodes are pruned here
+    std::vector<uint32_t> sched = build_schedule(log2n, log2par, extended, pruning == 3 ? 3 : pruning > 1 ? 1 : pruning, flags, &st);
     RawParams& p = L.p;
     p.sched = sched.data();
     p.llr = llr;
@@ -394,6 +395,7 @@ int emu_raw_decode(int fmt, int g, int log2n, int log2par, int llr_bits, int ext
     p.wpf = p.n >= 32 ? p.n / 32 : 1;
     p.q = (uint32_t)llr_bits;
     p.sigmag = fmt ? 1u : 0u;
+    p.log2par = (uint32_t)log2par;
     if (ls < 0 || ls > log2n - 1) ls = log2n - 1;
     if (log2n == 1) ls = 0;
     p.ls = (uint32_t)ls;

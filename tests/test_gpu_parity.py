@@ -226,6 +226,46 @@ def test_raw_kernel_configurations(scpd, fmt):
         assert (got == ol.decode_packed(n, 16, 6, 1, 1, flags, llr)).all()
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_reference_pruning_level2_mode(scpd, fmt):
+    """SCPD_PRUNE_REF_LEVEL2: the decoder the reference is as checked in (PRUNING_LEVEL 2: R0 / R1 / REP / SPC / H0),
+    bit-exact against sco_decode_l2, which tests/test_oracle.py pins on eleven builds of the reference's own sources.
+    It is not plain SC: the same frames decoded with SCPD_PRUNE_R0_R1 differ on some of the noisy ones."""
+    import torch
+    rng = np.random.default_rng(90 + fmt)
+    differs = 0
+    for key, nfr in (("c1", 400), ("c2", 120), ("c3", 6)):
+        name, n, k, snr = CONFIG_SETS[key]
+        flags = scpd.packed_flags(name, n)
+        cases = [(16, 8, 1), (16, 6, 1), (4, 8, 1), (64, 7, 0), (256, 9, 1), (2, 8, 1)] if key != "c3" else [(16, 8, 1)]
+        for par, q, ext in cases:
+            m = min(2 ** (q - 1) - 1, 127)
+            llr = np.concatenate([ol.channel(n, nfr, ol.sigma(snr - 1.5, k / n)),
+                                  rng.integers(-m, m + 1, size=(nfr // 4 + 1, n)).astype(np.int8),
+                                  rng.integers(-2, 3, size=(nfr // 4 + 1, n)).astype(np.int8), np.zeros((1, n), np.int8)])
+            dec = scpd.Decoder(n, k, flags, par=par, llr_bits=q, fmt=fmt, extended=ext, pruning=scpd.PRUNE_REF_LEVEL2)
+            assert "raw" in dec.kernel_name
+            want = ol.pack_bits(ol.decode_l2(n, par, q, fmt, ext, flags, llr))
+            got = dec.decode(torch.from_numpy(llr).cuda()).cpu().numpy().view(np.uint32)
+            assert (got == want).all(), (key, par, q, ext)
+            assert (dec.decode_host(llr[:33]) == want[:33]).all()
+            dec.close()
+            if (par, q, ext) == (16, 8, 1) and key != "c3":
+                plain = scpd.Decoder(n, k, flags, fmt=fmt).decode_host(llr)
+                differs += int((plain != want).any(axis=1).sum())
+    assert differs > 0
+    # the Monte-Carlo loop in that mode: the reference testbench as it ships (c1, golden codeword cycle)
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    cws = ol.golden_codewords()["cw1024x512"]
+    q = 6 if fmt else 8
+    dec = scpd.Decoder(n, k, flags, llr_bits=q, fmt=fmt, pruning=scpd.PRUNE_REF_LEVEL2)
+    got = dec.run_ber(1.5, k / n, 3000, codeword=cws[0])
+    llr = ol.channel(n, 3000, ol.sigma(1.5, k / n), codeword=cws[0])
+    want = ol.count_errors(n, ol.decode_l2(n, 16, q, fmt, 1, flags, llr), ref=cws[0])
+    assert list(got[:4]) == want[:4] and want[1] > 0
+
+
 def test_c1_headline_many_frames(scpd):
     """>= 10^5 noisy frames of BASELINE config 1 at 2.5 dB (BASELINE.md parity gate), odd batch."""
     name, n, k, snr = CONFIG_SETS["c1"]

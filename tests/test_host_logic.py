@@ -185,6 +185,92 @@ def test_raw_kernel_source_under_warp_emulator(fmt, q):
             assert (got == want).all(), (n, par, ext, g, "workspace")
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_reference_pruning_mode_under_warp_emulator(fmt):
+    """SCPD_PRUNE_REF_LEVEL2 (the reference built with PRUNING_LEVEL 2: R0 / R1 / REP / SPC / H0) on decode_raw.cuh,
+    lane by lane on the CPU, against sco_decode_l2 -- itself pinned on eleven builds of the reference's own sources
+    (test_oracle.py).  PAR 2 ... 256, LLR_BITS 6 ... 9, EXTENDED 0/1, 8 / 32 lanes per frame; noisy frames, the whole
+    Q-bit range, near-zero LLRs (ties in the minimum search, zero sums); storage split over shared memory / workspace."""
+    rng = np.random.default_rng(40 + fmt)
+    differs = 0
+    for tab, n, k in (("FB_N8_K4", 8, 4), ("FB_N512_K256", 512, 256), ("FB_N1024_K512", 1024, 512),
+                      ("frozen_n_4096_k_3072", 4096, 3072)):
+        flags = scpd.packed_flags(tab, n)
+        for par, q, ext, g in ((16, 8, 1, 32), (4, 9, 1, 8), (64, 6, 0, 32), (2, 7, 1, 8), (256, 8, 1, 32)):
+            if 2 * par > n or (n == 4096 and par not in (16, 64)):
+                continue
+            m = min(2 ** (q - 1) - 1, 127)
+            llr = np.concatenate([ol.channel(n, 2, ol.sigma(1.0 if k / n < 0.6 else 3.0, k / n)),
+                                  rng.integers(-m, m + 1, size=(2, n)).astype(np.int8),
+                                  rng.integers(-2, 3, size=(2, n)).astype(np.int8), np.zeros((1, n), np.int8)])
+            want = ol.pack_bits(ol.decode_l2(n, par, q, fmt, ext, flags, llr))
+            assert (_remu(fmt, g, flags, n, par, q, ext, 3, llr) == want).all(), (n, par, q, ext, g)
+            differs += int((ol.decode_packed(n, par, q, fmt, ext, flags, llr) != want).any(axis=1).sum())
+            if n == 512 and par == 16:
+                got = _remu(fmt, g, flags, n, par, q, ext, 3, llr, ls=5, beta_sm=0, warps=2, grid=2)
+                assert (got == want).all(), "workspace"
+    assert differs > 10  # the mode is a different decoder, and these inputs show it
+
+
+def test_reference_pruning_mode_stage_matrix_and_validation():
+    """scpd_stage_profile at SCPD_PRUNE_REF_LEVEL2 is the reference FSM at PRUNING_LEVEL 2: an independent recursion over
+    the frozen table counts the same F / F_REP / G / G_R1 / G_SPC / H / R visits; the mode needs 2 <= PAR <= 256."""
+    n, k, par = 1024, 512, 16
+    flags = scpd.packed_flags("FB_N1024_K512", n)
+
+    def wtype(o):
+        w = flags[o:o + par]
+        c = int(w.sum())
+        return "R0" if c == 0 else "R1" if c == par else "REP" if (c == 1 and w[-1]) else "SPC" if (c == par - 1 and not w[0]) else "RN"
+
+    def ctype(o, size):
+        t = [wtype(o + i) for i in range(0, size, par)]
+        if all(x == "R0" for x in t):
+            return "R0"
+        if all(x == "R1" for x in t):
+            return "R1"
+        if all(x == "R0" for x in t[:-1]) and t[-1] == "REP":
+            return "REP"
+        if t[0] == "SPC" and all(x == "R1" for x in t[1:]):
+            return "SPC"
+        return "RN"
+
+    acc = dict.fromkeys(scpd.STAGE_FUNCS, 0)
+
+    def rec(o, size, root=False):
+        if size <= par:
+            acc["R"] += 1
+            return
+        h = size // 2
+        tl, tr = ("RN", "RN") if root else (ctype(o, h), ctype(o + h, h))
+        if tl == "R0":
+            acc["R0"] += 1
+        elif tl == "REP":
+            acc["REP"] += 1
+        else:
+            acc["F"] += 1
+            rec(o, h)
+        if tr == "R1":
+            acc["R1"] += 1
+        elif tr == "SPC":
+            acc["SPC"] += 1
+        else:
+            acc["G"] += 1
+            rec(o + h, h)
+        acc["H"] += 1
+
+    rec(0, n, True)
+    vis, it, total = scpd.stage_profile(n, k, flags, par=par, pruning=scpd.PRUNE_REF_LEVEL2)
+    assert {f: int(vis[i].sum()) for i, f in enumerate(scpd.STAGE_FUNCS)} == acc
+    assert acc["REP"] > 0 and acc["SPC"] > 0 and acc["R1"] > 0
+    plain = scpd.stage_profile(n, k, flags, par=par, pruning=scpd.PRUNE_NONE)[2]
+    assert total < plain * 4 // 5  # why the reference ships with it: 484 instead of 640 loop trips per frame at c1
+    for bad_par in (1, 512):
+        with pytest.raises(scpd.ScpdError) as e:
+            scpd.Decoder(n, k, flags, par=bad_par, pruning=scpd.PRUNE_REF_LEVEL2)
+        assert e.value.status == scpd.E_CONFIG
+
+
 def test_stage_profile_matches_reference_fsm_trip_counts():
     """scpd_stage_profile (host only): at PRUNE_NONE the matrix is the reference FSM at PRUNING_LEVEL 0 -- every node
     above the leaf runs f_loop, g_loop and h_loop for half its PAR-wide words (my_module.h:343,373,704,903) and every

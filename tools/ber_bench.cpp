@@ -3,7 +3,8 @@
 // Unlike main.cpp (no arguments, macros), everything is a run-time option.
 //
 //   ber_bench --order FILE | --flags FILE  -n N -k K [--par 16] [--q 8] [--sm] [--no-ext]
-//             [--prune 0|1|2] [--snr 2.5[:step:stop]] [--rate R] [--frames F] [--seed 0xF0] [--device D]
+//             [--prune 0|1|2|3]  (3 = the reference's PRUNING_LEVEL 2 decoder: R0 / R1 / REP / SPC, not plain SC)
+//             [--snr 2.5[:step:stop]] [--rate R] [--frames F] [--seed 0xF0] [--device D]
 //             [--gpus G]   (frames split over G devices as independent streams; counters summed)
 //             [--monitor]  (print the function x level matrix of sc_monitor.h for this table and exit; no GPU needed)
 //             [--json]     (one JSON line per Eb/N0 point: counters, per-GPU counters, seconds, Gb/s)
@@ -69,7 +70,7 @@ int main(int argc, char** argv) {
             if (scpd_stage_profile(&cfg, flags.data(), &m) != SCPD_OK) throw std::runtime_error("bad configuration");
             int top = 0;
             while ((1u << top) < n) top++;
-            static const char* names[SCPD_STAGE_FUNCS] = {"F", "G", "H", "R", "R_R0", "R_R1"};
+            static const char* names[SCPD_STAGE_FUNCS] = {"F", "G", "H", "R", "R_R0", "R_R1", "F_REP", "G_SPC"};
             std::printf("[MONITOR] loop iterations per frame : %llu (pruning %u)\n", (unsigned long long)m.total_iterations, prune);
             std::printf("  Level     |");
             for (int l = top; l >= 0; l--) std::printf("%8u", 1u << l);

@@ -35,7 +35,8 @@ if a.check:
     import oracle_lib as ol
     idx = np.unique(np.concatenate([np.arange(min(a.check, a.frames)), np.arange(max(0, a.frames - a.check), a.frames)]))
     got = out.cpu().numpy().view(np.uint32)[idx]
-    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr.cpu().numpy()[idx], threads=8)
+    want = (ol.pack_bits(ol.decode_l2(n, 16, 8, 0, 1, flags, llr.cpu().numpy()[idx])) if a.prune == 3 else
+            ol.decode_packed(n, 16, 8, 0, 1, flags, llr.cpu().numpy()[idx], threads=8))
     print("check", len(idx), "frames:", "OK" if (got == want).all() else "MISMATCH")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
