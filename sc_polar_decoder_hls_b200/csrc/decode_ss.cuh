@@ -73,6 +73,11 @@ struct SsParams {
     unsigned long long ws_stride;  // uint4 per warp
     uint32_t ws_beta_off;
     uint32_t aoff[24];
+    // the leading f chain F(log2n), F(log2n - 1), ... of the schedule is computed by ss_planes_kernel (it depends on the
+    // channel alone): alpha[l] of the leftmost node, l = lpre .. log2n, sits at planes + poff[l] (poff[log2n] = 0,
+    // lpre = log2n: nothing prefused) and the walk starts below it
+    uint32_t lpre;
+    uint32_t poff[24];
     // != nullptr: per (function, level) SM-clock cycles [6][32] and visits [6][32] of warp 0 of every CTA (scpd_stage_time)
     unsigned long long* prof;
 };
@@ -520,9 +525,12 @@ struct SsThread {
     SS_DEV SsThread(const SsParams& p_) : p(p_) {}
 
     SS_DEV uint4* aptr(uint32_t l) const {  // not for l == p.ltm (tensor memory)
-        if (l == p.log2n) return const_cast<uint4*>(pl);
         return (l <= p.lsa ? sm : wsl) + p.aoff[l];
     }
+    // alpha[l] of the node whose first partial-sum word is wd: the root and the prefused leftmost nodes come from the
+    // task's plane buffer
+    SS_DEV bool in_planes(uint32_t l, uint32_t wd) const { return wd == 0u && l >= p.lpre; }
+    SS_DEV const uint4* asrc(uint32_t l, uint32_t wd) const { return in_planes(l, wd) ? pl + p.poff[l] : aptr(l); }
     // partial sums of node level l, word w: component w & 3 of a quad
     SS_DEV uint4* bquad(uint32_t l, uint32_t w) const {
         if (l < p.lwin) return sm + p.sm_beta_off + (((w & (p.win_words - 1u)) >> 2) * 32u);
@@ -609,7 +617,7 @@ struct SsThread {
     // (alpha levels in the workspace / plane buffer answer from L2 or DRAM).
     template <bool G, bool SRC_TM, bool DST_TM>
     SS_DEV void op_x(uint32_t l, uint32_t wd, bool zero) {
-        const uint4* src = SRC_TM ? nullptr : aptr(l);
+        const uint4* src = SRC_TM ? nullptr : asrc(l, wd);
         uint4* dst = DST_TM ? nullptr : aptr(l - 1);
         const uint32_t half = 1u << (l - 6);
         const uint32_t* ub = (G && !zero) ? bword(l - 1, wd) : nullptr;  // words wd .. wd + half - 1 lie in one storage
@@ -635,7 +643,7 @@ struct SsThread {
     }
     template <bool G>
     SS_DEV void op_fg(uint32_t l, uint32_t wd, bool zero) {
-        if (l == p.ltm)
+        if (l == p.ltm && !in_planes(l, wd))
             op_x<G, true, false>(l, wd, zero);
         else if (l == p.ltm + 1u)
             op_x<G, false, true>(l, wd, zero);
@@ -687,7 +695,7 @@ struct SsThread {
     // hard decision of alpha[l]; returns true (warp-uniform) when some LLR of some frame is zero
     template <bool SRC_TM>
     SS_DEV bool op_hd_x(uint32_t l, uint32_t wd) {
-        const uint4* src = SRC_TM ? nullptr : aptr(l);
+        const uint4* src = SRC_TM ? nullptr : asrc(l, wd);
         const uint32_t nc = 1u << (l - 5);
         uint4* d = bquad(l, wd);
         uint32_t z = 0u;
@@ -708,7 +716,9 @@ struct SsThread {
         }
         return SS_ANY(z != 0u);
     }
-    SS_DEV bool op_hd(uint32_t l, uint32_t wd) { return l == p.ltm ? op_hd_x<true>(l, wd) : op_hd_x<false>(l, wd); }
+    SS_DEV bool op_hd(uint32_t l, uint32_t wd) {
+        return (l == p.ltm && !in_planes(l, wd)) ? op_hd_x<true>(l, wd) : op_hd_x<false>(l, wd);
+    }
 
     // ---------------------------------------------------------------- nodes of 64 and 32 LLRs
     // partial-sum word of a node of 32 LLRs given as one chunk of planes (out of line: one copy of the walker)
@@ -765,7 +775,7 @@ struct SsThread {
             load(aptr(6), r0);
             load(aptr(6) + 64, r1);
         } else {
-            const uint4* src = aptr(7);
+            const uint4* src = asrc(7, wd & ~3u);  // N = 128: the root
             V a0, b0, a1, b1;
             load(src, a0);
             load(src + 128, b0);
@@ -856,42 +866,101 @@ struct SsThread {
     }
 };
 
+// int8 rows -> sign-magnitude planes in the chunk layout of the decode kernel (wrapper_in.h:30-42), plus the first D
+// f levels of the tree, which depend on the channel alone: alpha[log2n - s] of the leftmost node, s = 1 .. D, so that the
+// walk kernel neither runs those f ops nor reads the channel planes for them (the conversion is bound by DRAM, its ALUs
+// are idle).  One call = one lane (frame) and one unit of 8 chunks: 2^D groups, C >> D chunks apart, of 8 >> D
+// consecutive chunks, i.e. every operand of the D-level f tree over them.  Level s pairs entries 8 >> s apart.
+struct SsPre {
+    uint32_t off[4];  // off[s]: uint4 offset of alpha[log2n - s] of the leftmost node in the task's plane buffer
+};
+namespace ss {
+template <int P, int D>
+SS_DEV void planes_unit(const int8_t* row, bool valid, uint32_t nchunks, uint32_t unit, uint4* dst, const SsPre& pre) {
+    constexpr uint32_t PER = 8u >> D;
+    const uint32_t gstride = nchunks >> D, cb = unit * PER;
+    bs::Val<P> x[8];
+    auto put = [&](uint4* base, uint32_t c, const bs::Val<P>& r) {
+        uint32_t o[8];
+        o[0] = r.s;
+#pragma unroll
+        for (int k = 1; k < 8; k++) o[k] = k <= P ? r.m[k - 1] : 0u;
+        base[(2u * c) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+        base[(2u * c + 1u) * 32u] = make_uint4(o[4], o[5], o[6], o[7]);
+    };
+#pragma unroll
+    for (uint32_t a = 0; a < 8u; a++) {
+        const uint32_t c = (a / PER) * gstride + cb + (a % PER);
+        uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (valid) {
+#if defined(__CUDA_ARCH__)
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(row + 32u * c));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(row + 32u * c) + 1);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+            v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+#else
+            for (int k = 0; k < 8; k++) {
+                uint32_t t = 0;
+                for (int b = 0; b < 4; b++) t |= (uint32_t)(uint8_t)row[32u * c + 4 * k + b] << (8 * b);
+                v[k] = t;
+            }
+#endif
+        }
+        chunk_planes<P>(v, x[a]);
+        put(dst, c, x[a]);
+    }
+#pragma unroll
+    for (int s = 1; s <= D; s++) {
+        const uint32_t dist = 8u >> s;
+#pragma unroll
+        for (uint32_t a = 0; a < dist; a++) {
+            bs::Val<P> r;
+            bs::f_op<P>(x[a], x[a + dist], r);
+            x[a] = r;
+            put(dst + pre.off[s], (a / PER) * gstride + cb + (a % PER), r);
+        }
+    }
+}
+}  // namespace ss
+
 #if defined(__CUDACC__)
-// int8 rows -> sign-magnitude planes in the chunk layout of the decode kernel.        wrapper_in.h:30-42
-// One warp per (task, 8 chunks); lane = frame: 32 bytes of the lane's row per chunk.
-template <int Q>
+// One warp per (task, unit); lane = frame: 32 bytes of the lane's row per chunk.
+template <int Q, int D>
 __global__ void __launch_bounds__(256) ss_planes_kernel(const int8_t* __restrict__ llr, unsigned long long nframes, uint32_t n,
-                                                        uint4* __restrict__ planes, unsigned long long planes_stride) {
+                                                        uint4* __restrict__ planes, unsigned long long planes_stride,
+                                                        const SsPre pre) {
     constexpr int P = Q - 1;
     const int lane = threadIdx.x & 31;
     const unsigned long long ntasks = (nframes + 31) / 32;
-    const uint32_t blocks_per_task = n / 256u;  // n >= 256; n = 128 handled by the tail below
-    const unsigned long long nunits = ntasks * (blocks_per_task ? blocks_per_task : 1u);
+    const uint32_t units_per_task = n / 256u;  // n >= 256; n = 128 handled by the tail below (D = 0)
+    const unsigned long long nunits = ntasks * (units_per_task ? units_per_task : 1u);
     const unsigned long long wstride = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     for (unsigned long long t = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < nunits; t += wstride) {
-        const unsigned long long task = blocks_per_task ? t / blocks_per_task : t;
-        const uint32_t c0 = blocks_per_task ? (uint32_t)(t % blocks_per_task) * 8u : 0u;
-        const uint32_t nc = blocks_per_task ? 8u : n / 32u;
+        const unsigned long long task = units_per_task ? t / units_per_task : t;
         const unsigned long long f = task * 32ull + lane;
         const bool valid = f < nframes;
         const int8_t* row = llr + (valid ? f : 0ull) * n;
         uint4* dst = planes + task * planes_stride + lane;
-        for (uint32_t c = c0; c < c0 + nc; c++) {
-            uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            if (valid) {
-                const uint4 x = __ldg(reinterpret_cast<const uint4*>(row + 32u * c));
-                const uint4 y = __ldg(reinterpret_cast<const uint4*>(row + 32u * c) + 1);
-                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-                v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-            }
-            bs::Val<P> x;
-            ss::chunk_planes<P>(v, x);
-            uint32_t o[8];
-            o[0] = x.s;
+        if (units_per_task) {
+            ss::planes_unit<P, D>(row, valid, n / 32u, (uint32_t)(t % units_per_task), dst, pre);
+        } else {
+            for (uint32_t c = 0; c < n / 32u; c++) {
+                uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                if (valid) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(row + 32u * c));
+                    const uint4 y = __ldg(reinterpret_cast<const uint4*>(row + 32u * c) + 1);
+                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+                }
+                bs::Val<P> x;
+                ss::chunk_planes<P>(v, x);
+                uint32_t o[8];
+                o[0] = x.s;
 #pragma unroll
-            for (int k = 1; k < 8; k++) o[k] = k <= P ? x.m[k - 1] : 0u;
-            dst[(2u * c) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[(2u * c + 1u) * 32u] = make_uint4(o[4], o[5], o[6], o[7]);
+                for (int k = 1; k < 8; k++) o[k] = k <= P ? x.m[k - 1] : 0u;
+                dst[(2u * c) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[(2u * c + 1u) * 32u] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
         }
     }
 }

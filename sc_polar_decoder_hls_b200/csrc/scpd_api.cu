@@ -158,6 +158,7 @@ struct scpd_decoder {
     uint8_t* d_bs_planes = nullptr;
     size_t bs_planes_bytes = 0;
     // slot-sliced kernel plan (decode_ss.cuh): lane = frame; ss_ok == false: not available for this configuration
+    int ss_pre = 0;  // leading f levels computed by the plane conversion
     bool ss_ok = false;
     int ss_warps = 16;
     int ss_max_log2n = 14;
@@ -333,6 +334,12 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
         return SCPD_OK;
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * d->ss_warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the leading f ops of the walk depend on the channel alone: the plane conversion computes them (decode_ss.cuh).
+    // Measured (profiles/tuning_r2.md): c2 385 -> 419 -> 424 Gb/s for 0 / 1 / 2 levels (the walk is DRAM-bound there and
+    // reads the planes once less), c1 362 -> 357 -> 349 (its level 9 would leave tensor memory): on from N = 2048
+    d->ss_pre = ss_prefuse_depth(d->ss_sched_host, d->log2n, d->ss_plan.lsa,
+                                 env_int("SCPD_SS_PRE", d->log2n >= 12 ? 2 : d->log2n == 11 ? 1 : 0));
+    d->ss_sched_host.erase(d->ss_sched_host.begin(), d->ss_sched_host.begin() + d->ss_pre);
     d->ss_ok = true;
     d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", 14);
     d->ss_min_tasks = (unsigned long long)env_int("SCPD_SS_MIN_TASKS", 4 * d->num_sms);
@@ -842,17 +849,28 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     const unsigned long long grid = std::min<unsigned long long>((unsigned long long)d->num_sms, (ntasks + warps - 1) / warps);
     int rc = grow((void**)&d->d_ss_ws, &d->ss_ws_bytes, (size_t)(grid * warps * d->ss_plan.ws_stride * 16ull) + 16, st);
     if (rc) return rc;
-    const size_t pl_stride = ss_planes_quads(d->log2n);
+    SsPre pre;
+    const size_t pl_stride = ss_planes_quads(d->log2n, d->ss_pre, pre.off);
     rc = grow((void**)&d->d_ss_planes, &d->ss_planes_bytes, (size_t)ntasks * pl_stride * 16, st);
     if (rc) return rc;
     {
         const unsigned long long units = ntasks * std::max<unsigned long long>(1, d->cfg.n / 256u);
         const unsigned blocks = (unsigned)std::min<unsigned long long>((units + 7) / 8, (unsigned long long)d->num_sms * 32);
+#define SS_PLANES(Q, D) ss_planes_kernel<Q, D><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride, pre)
+#define SS_PLANES_Q(Q)                   \
+    switch (d->ss_pre) {                 \
+        case 1: SS_PLANES(Q, 1); break;  \
+        case 2: SS_PLANES(Q, 2); break;  \
+        case 3: SS_PLANES(Q, 3); break;  \
+        default: SS_PLANES(Q, 0); break; \
+    }
         switch (d->cfg.llr_bits) {
-            case 6: ss_planes_kernel<6><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride); break;
-            case 7: ss_planes_kernel<7><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride); break;
-            default: ss_planes_kernel<8><<<blocks, 256, 0, st>>>(d_llr, nframes, d->cfg.n, d->d_ss_planes, pl_stride); break;
+            case 6: SS_PLANES_Q(6) break;
+            case 7: SS_PLANES_Q(7) break;
+            default: SS_PLANES_Q(8) break;
         }
+#undef SS_PLANES_Q
+#undef SS_PLANES
         d->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -878,6 +896,9 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.ws_stride = d->ss_plan.ws_stride;
     p.ws_beta_off = d->ss_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->ss_plan.aoff[l];
+    p.lpre = (uint32_t)(d->log2n - d->ss_pre);
+    for (int l = 0; l < 24; l++) p.poff[l] = 0u;
+    for (int s = 1; s <= d->ss_pre; s++) p.poff[d->log2n - s] = pre.off[s];
     p.prof = d->d_ss_prof;
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->d_ss_prof != nullptr);

@@ -250,7 +250,25 @@ struct SsPlan {
     unsigned long long ws_stride = 0;  // per warp
     uint32_t win_words = 0;
 };
-static inline size_t ss_planes_quads(int log2n) { return (size_t)64u << (log2n - 5); }  // uint4 per 32-frame task
+// uint4 per 32-frame task: the channel planes, then alpha[log2n - s] of the leftmost node for s = 1 .. pre (the leading
+// f chain computed by ss_planes_kernel); off[s] = where level log2n - s starts
+static inline size_t ss_planes_quads(int log2n, int pre = 0, uint32_t* off = nullptr) {
+    size_t q = 0;
+    for (int s = 0; s <= pre; s++) {
+        if (off) off[s] = (uint32_t)q;
+        q += (size_t)64u << (log2n - s - 5);
+    }
+    return q;
+}
+// How many leading ops of the schedule are F(log2n, 0), F(log2n - 1, 0), ... whose result neither lives on chip (level
+// above lsa) nor is smaller than a unit of the plane kernel: those are stripped and computed by ss_planes_kernel.
+static inline int ss_prefuse_depth(const std::vector<uint32_t>& ops, int log2n, uint32_t lsa, int max_depth) {
+    int d = 0;
+    while (d < max_depth && d < 3 && (size_t)d < ops.size() && ss_op_code(ops[d]) == SS_F && (int)ss_op_level(ops[d]) == log2n - d &&
+           ss_op_word(ops[d]) == 0u && log2n - d - 1 > (int)lsa && log2n - d - 1 >= 8 && log2n >= 8)
+        d++;
+    return d;
+}
 
 // smem_per_warp in bytes.  Returns false when even the minimum (alpha[6] + a 256-position window) does not fit.
 // tm_cols_avail: tensor-memory columns a warp may use (512 / ceil(warps per CTA / 4)), 0 = do not use tensor memory;

@@ -2,7 +2,7 @@
 // compiled as plain C++ through tests/emu/fake_cuda/cuda_runtime.h) on the CPU.  Every lane of that kernel owns
 // one frame and shares nothing with its neighbours but the schedule, so the emulation is a loop over lanes; the
 // warp vote of the all-information shortcut degenerates to the lane's own flag (both branches give the same bits,
-// which is what the tests check) unless `vote` asks for the whole-warp OR, computed here in a first pass.
+// which is what the tests check).
 // fp16x2 arithmetic is emulated with exact float pairs (decode_ss.cuh, host branch).  Never a decode path.
 #include <cstdio>
 #include <cstdlib>
@@ -25,11 +25,11 @@ using namespace scpd;
 
 template <int Q, int LOG2PAR, bool EXT>
 static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, size_t nframes, uint32_t* xhat,
-               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats, int ltm) {
+               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats, int ltm, int max_pre) {
     constexpr int P = Q - 1;
     const uint32_t n = 1u << log2n;
     SsStats st;
-    const std::vector<uint32_t> sched = ss_build_schedule(log2n, pruning, flags, &st, fuse);
+    std::vector<uint32_t> sched = ss_build_schedule(log2n, pruning, flags, &st, fuse);
     if (stats) {
         stats[0] = st.n_ops;
         stats[1] = st.n_f;
@@ -40,11 +40,28 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     if (!ss_make_plan(log2n, smem_per_warp, &plan, force_lsa, force_lwin, ltm ? 512u : 0u, ltm)) return 1;
     if (ltm > 0 && plan.ltm != (uint32_t)ltm) return 3;
     const size_t ntasks = (nframes + 31) / 32;
-    const size_t pl_stride = ss_planes_quads(log2n);
-    std::vector<uint4> planes(ntasks * pl_stride, uint4{0, 0, 0, 0});
+    // the leading f ops are computed with the planes (scpd_api.cu: plan_ss / decode_ss)
+    const int pre = ss_prefuse_depth(sched, log2n, plan.lsa, max_pre);
+    sched.erase(sched.begin(), sched.begin() + pre);
+    if (stats) stats[4] = (uint64_t)pre;
+    SsPre pre_off;
+    const size_t pl_stride = ss_planes_quads(log2n, pre, pre_off.off);
+    std::vector<uint4> planes(ntasks * pl_stride, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     // ss_planes_kernel, lane by lane
     for (size_t f = 0; f < nframes; f++) {
         uint4* dst = planes.data() + (f / 32) * pl_stride + (f % 32);
+        if (n >= 256) {
+            for (uint32_t u = 0; u < n / 256; u++) {
+                const int8_t* row = llr + f * n;
+                switch (pre) {
+                    case 1: ss::planes_unit<P, 1>(row, true, n / 32, u, dst, pre_off); break;
+                    case 2: ss::planes_unit<P, 2>(row, true, n / 32, u, dst, pre_off); break;
+                    case 3: ss::planes_unit<P, 3>(row, true, n / 32, u, dst, pre_off); break;
+                    default: ss::planes_unit<P, 0>(row, true, n / 32, u, dst, pre_off); break;
+                }
+            }
+            continue;
+        }
         for (uint32_t c = 0; c < n / 32; c++) {
             uint32_t v[8];
             std::memcpy(v, llr + f * n + 32u * c, 32);
@@ -79,6 +96,8 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     p.ws_stride = plan.ws_stride;
     p.ws_beta_off = plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = plan.aoff[l];
+    p.lpre = (uint32_t)(log2n - pre);
+    for (int s = 1; s <= pre; s++) p.poff[log2n - s] = pre_off.off[s];
     std::vector<uint4> smem(plan.sm_stride, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     std::vector<uint4> ws(plan.ws_stride ? plan.ws_stride : 1, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     p.ws = ws.data();
@@ -100,16 +119,15 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
 
 extern "C" int ss_emu_decode(int log2n, int q, int log2par, int ext, int pruning, const uint8_t* flags, const int8_t* llr,
                              size_t nframes, uint32_t* xhat, size_t smem_per_warp, int force_lsa, int force_lwin, int fuse,
-                             uint64_t* stats, int ltm) {
+                             uint64_t* stats, int ltm, int max_pre) {
 #define SS_CASE(Q, LP, E)                          \
     if (q == Q && log2par == LP && ext == (E ? 1 : 0)) \
-        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats, ltm);
+        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats, ltm, max_pre);
     SS_CASE(8, 4, true)
     SS_CASE(8, 4, false)
     SS_CASE(6, 4, true)
     SS_CASE(7, 4, true)
     SS_CASE(8, 2, true)
-    SS_CASE(8, 5, true)
     SS_CASE(8, 3, true)
     SS_CASE(6, 2, false)
 #undef SS_CASE

@@ -13,13 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = {}
 
 
-def ss_emu(flags, n, par, q, ext, prune, llr, smem=18 * 1024, lsa=-1, lwin=-1, fuse=1, ltm=0):
+def ss_emu(flags, n, par, q, ext, prune, llr, smem=18 * 1024, lsa=-1, lwin=-1, fuse=1, ltm=0, pre=2):
     if "l" not in _LIB:
         _LIB["l"] = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libss_emu.so"))
     out = np.zeros((len(llr), n // 32), np.uint32)
-    st = (ctypes.c_uint64 * 4)()
+    st = (ctypes.c_uint64 * 5)()
     rc = _LIB["l"].ss_emu_decode(int(np.log2(n)), q, int(np.log2(par)), ext, prune, ol.P(flags), ol.P(llr),
-                                 ctypes.c_size_t(len(llr)), ol.P(out), ctypes.c_size_t(smem), lsa, lwin, fuse, st, ltm)
+                                 ctypes.c_size_t(len(llr)), ol.P(out), ctypes.c_size_t(smem), lsa, lwin, fuse, st, ltm, pre)
     assert rc == 0, rc
     return out, [int(v) for v in st]
 
@@ -87,3 +87,28 @@ def test_ss_known_patterns_cover_the_packaged_tables():
         f = scpd.packed_flags(name, n).reshape(-1, 8)
         pats = set(np.packbits(f, axis=1, bitorder="little").ravel().tolist())
         assert pats <= known, (name, pats - known)
+
+
+@pytest.mark.parametrize("name,n,k", [("FB_N512_K256", 512, 256), ("FB_N1024_K512", 1024, 512), ("frozen_n_4096_k_3072", 4096, 3072)])
+def test_ss_leading_f_levels_computed_with_the_planes(name, n, k):
+    """The first f ops of the walk depend on the channel alone: ss_planes_kernel computes them (0 ... 3 levels) and the
+    schedule starts below; the leftmost nodes are then read from the plane buffer, also when their level otherwise
+    lives in tensor memory, and a table whose left half is all-frozen (no leading f) prefuses nothing."""
+    flags = scpd.packed_flags(name, n)
+    llr = _llrs(np.random.default_rng(n), n, k, 8, nfr=8)
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+    depths = set()
+    for pre in (0, 1, 2, 3):
+        for ltm in (0, int(np.log2(n)) - 1):
+            for prune in (0, 2):
+                got, st = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=10 * 1024, ltm=ltm if ltm >= 8 else 0, pre=pre)
+                assert (got == want).all(), (pre, ltm, prune)
+                assert st[4] <= pre
+                depths.add(st[4])
+    assert max(depths) >= (1 if n == 512 else 2)
+    half = flags.copy()
+    half[:n // 2] = 0
+    got, st = ss_emu(half, n, 16, 8, 1, 2, llr, pre=3)
+    assert st[4] == 0 and (got == ol.decode_packed(n, 16, 8, 0, 1, half, llr)).all()
+    got, st = ss_emu(np.ones(n, np.uint8), n, 16, 8, 1, 2, llr, pre=3)   # all-information root: hard decision first
+    assert st[4] == 0 and (got == ol.decode_packed(n, 16, 8, 0, 1, np.ones(n, np.uint8), llr)).all()
