@@ -161,7 +161,7 @@ struct scpd_decoder {
     int ss_pre = 0;  // leading f levels computed by the plane conversion
     bool ss_ok = false;
     int ss_warps = 16;
-    int ss_max_log2n = 14;
+    int ss_max_log2n = 15;
     unsigned long long ss_min_tasks = 0;
     bool ss_sched_smem = false;
     SsPlan ss_plan;
@@ -341,7 +341,7 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
                                  env_int("SCPD_SS_PRE", d->log2n >= 12 ? 2 : d->log2n == 11 ? 1 : 0));
     d->ss_sched_host.erase(d->ss_sched_host.begin(), d->ss_sched_host.begin() + d->ss_pre);
     d->ss_ok = true;
-    d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", 14);
+    d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", 15);
     d->ss_min_tasks = (unsigned long long)env_int("SCPD_SS_MIN_TASKS", 4 * d->num_sms);
     if (env_int("SCPD_VERBOSE", 0))
         fprintf(stderr, "[scpd] slot-sliced kernel: %d warps/CTA, alpha levels 6..%u and partial sums below level %u in smem, "
@@ -957,9 +957,9 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (d->raw_only) return decode_raw(d, d_llr, nframes, d_xhat, st);
-    // The slot-sliced kernel (a lane per frame) is the default for CA2 up to N = 2^14 once the batch gives every SM
-    // a few warps (measured, profiles/tuning_r2.md: 347 / 384 Gb/s against 231 / 288 at N = 1024 / 4096; from N = 2^15
-    // its 32-frame workspace per warp costs more DRAM traffic than the frame-sliced kernel's, which wins there)
+    // The slot-sliced kernel (a lane per frame) is the default for CA2 up to N = 2^15 once the batch gives every SM
+    // a few warps (measured, profiles/tuning_r2.md: 364 / 423 / 303 Gb/s against 231 / 288 / 287 at N = 1024 / 4096 /
+    // 32768; from N = 2^17 its 32-frame workspace per warp costs more DRAM traffic than the frame-sliced kernel's)
     if (d->ss_ok && (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0 &&
         (d->kernel_pinned || (d->log2n <= d->ss_max_log2n && (nframes + 31) / 32 >= d->ss_min_tasks)))
         return decode_ss(d, d_llr, nframes, d_xhat, st);

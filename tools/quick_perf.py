@@ -10,7 +10,7 @@ import torch
 
 import sc_polar_decoder_hls_b200 as scpd
 
-SETS = {"c1": ("FB_N1024_K512", 1024, 512, 2.5), "c2": ("frozen_n_4096_k_3072", 4096, 3072, 3.5),
+SETS = {"n2048": ("FB_N2048_K1024", 2048, 1024, 2.5), "c1": ("FB_N1024_K512", 1024, 512, 2.5), "c2": ("frozen_n_4096_k_3072", 4096, 3072, 3.5),
         "c3": ("frozen_n_32768_k_29492_snr_4_5", 32768, 29492, 4.5),
         "c4": ("frozen_n_131072_k_117964", 131072, 117964, 4.5),
         "c5": ("frozen_n_524288_k_262144", 524288, 262144, 2.0)}
