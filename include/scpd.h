@@ -176,6 +176,12 @@ float scpd_sigma(float ebn0_db, float rate);
 int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nframes, uint8_t seed,
                           float sigma, const uint8_t* d_codeword, int per_frame, int8_t* d_llr,
                           void* cuda_stream);
+/* How the Box-Muller step of the channel (sc_awgn.h:61-77) is evaluated, process-wide; returns the previous mode.
+ * 0: logf / sqrtf / sincosf as libm-grade code.  2 (default): SFU approximations, with the libm-grade code re-run for
+ * every sample that lands within a guard band of a quantiser bin edge -- the same LLRs at about half the instructions
+ * (the band is 16x the largest deviation found over 8e10 draws, tools/probe/chan_err.cu).  1: approximations only (about
+ * 1e-5 of the LLRs differ by one quantiser step).  mode < 0 only reads the current mode. */
+int scpd_channel_mode(int mode);
 /* sc_error_counter.h:68-125.  d_ref_words: packed reference codeword(s) ([n/32] shared or
  * [nframes][n/32]) or NULL for all-zero.  d_counters (6 x uint64, accumulated, caller zeroes):
  * [0] bit errors [1] frame errors [2] bits [3] frames [4],[5] as [0],[1] with the reference's

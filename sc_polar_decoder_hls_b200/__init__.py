@@ -69,6 +69,7 @@ def _load():
         "scpd_last_kernel_name": (c.c_char_p, [vp]),
         "scpd_stage_profile": (c.c_int, [c.POINTER(Config), u8p, c.POINTER(StageMatrix)]),
         "scpd_sigma": (c.c_float, [c.c_float, c.c_float]),
+        "scpd_channel_mode": (c.c_int, [c.c_int]),
         "scpd_channel_generate": (c.c_int, [c.c_uint32, c.c_uint64, c.c_size_t, c.c_uint8, c.c_float, vp,
                                             c.c_int, vp, vp]),
         "scpd_count_errors": (c.c_int, [c.c_uint32, c.c_size_t, vp, vp, c.c_int, vp, vp]),
@@ -93,7 +94,7 @@ EXPORTS = ["scpd_frozen_load_order", "scpd_frozen_load_flags", "scpd_frozen_writ
            "scpd_frozen_write_flags", "scpd_write_polar_parameters", "scpd_create", "scpd_destroy",
            "scpd_decode", "scpd_decode_host", "scpd_validate_llr", "scpd_extract_info", "scpd_get_config",
            "scpd_schedule_stats", "scpd_launch_count", "scpd_kernel_timing", "scpd_last_kernel_ms",
-           "scpd_kernel_name", "scpd_last_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate",
+           "scpd_kernel_name", "scpd_last_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate", "scpd_channel_mode",
            "scpd_count_errors", "scpd_run_ber", "scpd_run_ber_ex", "scpd_stage_timing", "scpd_stage_time", "scpd_last_error",
            "scpd_status_string"]
 SRC_CODEWORDS, SRC_RANDOM = 0, 1
@@ -299,6 +300,12 @@ def payload_words(seed, first_frame, nframes, info_flags):
     flags[:n] = info_flags
     mask = np.packbits(flags, bitorder="little").view(np.uint32)
     return (z & np.uint64(0xFFFFFFFF)).astype(np.uint32) & mask[None, :]
+
+
+def channel_mode(mode=-1):
+    """scpd_channel_mode: 0 libm-grade Box-Muller, 2 guarded SFU approximations (default, same LLRs), 1 approximations
+    only; returns the previous mode (mode < 0: only reads it)."""
+    return int(lib.scpd_channel_mode(mode))
 
 
 def channel_generate(n, nframes, sigma_v, first_frame=0, seed=0xF0, codeword=None, device=0, stream=None):

@@ -83,8 +83,12 @@ __device__ __forceinline__ int quantize_llr(float y) {  // sc_quantizer.h:77-80 
 // [l c, (l + 1) c) of the block, c = F n / 64 = 2^log2c, i.e. 2c consecutive LLR bytes, 16 at a time.  The jump to the
 // block start and the 31-step chain that hands every lane its own stream position are paid once per block instead of
 // once per frame (at n = 1024 they cost four times the draws themselves).
-// fast != 0: logf / sinf / cosf through the SFU approximations (__logf, __sincosf): the uniform stream is the same,
-// the Gaussian samples differ in the last bits, a quantised LLR differs by one step on about 1e-5 of the samples.
+// fast = 0: logf / sqrtf / sincosf as libm-grade code (134 instructions per draw, the kernel is issue-bound at 85 %).
+// fast = 2 (default, "guarded"): the SFU approximations (__logf, rsqrtf, __sincosf) first; they land within 1.6e-5 sigma
+// quantiser steps of the libm-grade value when r1 <= 0.999 (tools/probe/chan_err.cu, 8e10 draws per sigma), so a sample
+// further than 2.5e-4 max(sigma, 1) from a bin edge of the quantiser has its bin decided; the others (and r1 > 0.999, where
+// the relative error of log explodes) are recomputed with the libm-grade code: same LLRs, about half the instructions.
+// fast = 1: approximations only (a quantised LLR differs by one step on about 1e-5 of the samples).
 __global__ void __launch_bounds__(128)
 channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nframes, uint32_t seed, float sigma,
                const uint8_t* __restrict__ codeword, int per_frame, int8_t* __restrict__ llr, XsJumpTable jt, int log2c,
@@ -117,6 +121,7 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
     const unsigned long long valid = (nframes - f0 < fpb ? nframes - f0 : (unsigned long long)fpb) * n;  // bytes of the block
     int8_t* out = llr + f0 * n;
     const float two_pi = __fmul_rn(2.0f, 3.14159265358979f);  // sc_awgn.h:61-62
+    const float guard = 2.5e-4f * fmaxf(sigma, 1.0f);
     const uint32_t nmask = n - 1u;
     const bool aligned = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
     // 16 bytes (8 draws) per store; a lane's range is a multiple of 16 bytes for every n >= 2 ... when 2c >= 16,
@@ -134,13 +139,14 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
             const float y = __fmul_rn(two_pi, r2);  // sc_awgn.h:67
             float x, sn, cs;
             if (fast) {
-                x = sqrtf(__fmul_rn(-2.0f, __logf(r1)));
+                const float t = __fmul_rn(-2.0f, __logf(r1));
+                x = __fmul_rn(t, rsqrtf(t));
                 __sincosf(y, &sn, &cs);
             } else {
                 x = sqrtf(__fmul_rn(-2.0f, logf(r1)));  // :68
                 sincosf(y, &sn, &cs);
             }
-            const float ph = __fmul_rn(x, sn), qu = __fmul_rn(x, cs);  // :74-77
+            float ph = __fmul_rn(x, sn), qu = __fmul_rn(x, cs);  // :74-77
             float s0 = 1.0f, s1 = 1.0f;  // sc_bpsk.h:53
             if (codeword) {
                 const unsigned long long i = i0 + 2u * k;
@@ -154,6 +160,18 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
                     const uint8_t* cw = per_frame ? codeword + (f0 + i / n) * n : codeword;
                     s0 = cw[pos] ? -1.0f : 1.0f;
                     s1 = cw[pos + 1] ? -1.0f : 1.0f;
+                }
+            }
+            if (fast == 2) {  // guarded: is the quantiser bin of both samples decided whatever the approximation error?
+                const float t0 = __fmul_rn(__fadd_rn(s0, __fmul_rn(ph, sigma)), 4.0f);
+                const float t1 = __fmul_rn(__fadd_rn(s1, __fmul_rn(qu, sigma)), 4.0f);
+                const bool edge0 = fabsf(t0 - rintf(t0)) < guard && fabsf(t0) < 33.0f;
+                const bool edge1 = fabsf(t1 - rintf(t1)) < guard && fabsf(t1) < 33.0f;
+                if (edge0 || edge1 || !(r1 <= 0.999f)) {
+                    x = sqrtf(__fmul_rn(-2.0f, logf(r1)));
+                    sincosf(y, &sn, &cs);
+                    ph = __fmul_rn(x, sn);
+                    qu = __fmul_rn(x, cs);
                 }
             }
             const int q0 = quantize_llr(__fadd_rn(s0, __fmul_rn(ph, sigma)));  // sc_adder.h:139-140

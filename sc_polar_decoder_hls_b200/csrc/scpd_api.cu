@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -1230,6 +1231,17 @@ extern "C" float scpd_sigma(float ebn0_db, float rate) {  // main.cpp:91-98
     return 1.0f / sqrtf(2.f * rate * powf(10.f, ebn0_db / 10.f));
 }
 
+// 2 = SFU approximations, libm-grade recomputation next to a quantiser bin edge (same LLRs; harness.cuh); 0 = libm-grade
+// only; 1 = approximations only.  SCPD_CHANNEL_FAST sets the initial value (read once).
+static std::atomic<int>& channel_mode() {
+    static std::atomic<int> mode(std::max(0, std::min(2, env_int("SCPD_CHANNEL_FAST", 2))));
+    return mode;
+}
+extern "C" int scpd_channel_mode(int mode) {
+    if (mode < 0) return channel_mode().load();
+    return channel_mode().exchange(std::min(mode, 2));
+}
+
 extern "C" int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nframes, uint8_t seed, float sigma,
                                      const uint8_t* d_codeword, int per_frame, int8_t* d_llr, void* stream) {
     if (nframes == 0) return SCPD_OK;
@@ -1245,9 +1257,8 @@ extern "C" int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nf
     const int log2c = ilog2(fpb * n / 64u);
     const unsigned long long nblk = (nframes + fpb - 1) / fpb;
     const unsigned grid = (unsigned)((nblk + 3) / 4);
-    static const int fast_math = env_int("SCPD_CHANNEL_FAST", 0);
     channel_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, d_codeword, per_frame,
-                                                           d_llr, jt, log2c, fpb, fast_math);
+                                                           d_llr, jt, log2c, fpb, channel_mode().load());
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
 }

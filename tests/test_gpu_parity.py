@@ -414,6 +414,33 @@ def test_slot_sliced_is_the_default_for_large_batches(scpd):
     assert "slot-sliced" in seen[32768] and "int16x2" in seen[2048], seen
 
 
+def test_channel_guarded_fast_path_gives_the_same_llrs(scpd):
+    """scpd_channel_mode: the default (2) evaluates Box-Muller with the SFU approximations and re-runs the libm-grade code
+    for samples next to a quantiser bin edge; it must produce the LLRs of mode 0 (libm-grade only) sample for sample --
+    here 2^29 of them over three noise levels, stored codewords and the all-zero one -- while mode 1 (approximations
+    only) differs on a few, which is what the guard band is for.  Mode 0 itself is checked against the host chain."""
+    import torch
+    cw = ol.golden_codewords()["cw1024x512"]
+    prev = scpd.channel_mode()
+    assert prev == 2
+    try:
+        unguarded = 0
+        for n, nfr, snr, cwsel in ((1024, 1 << 17, 0.5, cw[1]), (4096, 1 << 15, 3.5, None), (1024, 1 << 17, 6.0, cw[:2].repeat(1 << 16, axis=0))):
+            out = {}
+            for mode in (0, 2, 1):
+                scpd.channel_mode(mode)
+                out[mode] = scpd.channel_generate(n, nfr, scpd.sigma(snr, 0.5), first_frame=12345, codeword=cwsel)
+            torch.cuda.synchronize()
+            assert torch.equal(out[0], out[2]), (n, snr)
+            unguarded += int((out[0] != out[1]).sum())
+            host = ol.channel(n, 64, ol.sigma(snr, 0.5), first_frame=12345,
+                              codeword=None if cwsel is None else (cwsel if cwsel.ndim == 1 else cwsel[:64]))
+            assert (out[0][:64].cpu().numpy() == host).all()
+        assert 0 < unguarded < 20000  # ~1e-5 of 4e8 samples
+    finally:
+        scpd.channel_mode(prev)
+
+
 def test_validate_llr_counts_contract_violations(scpd):
     import torch
     name, n, k, snr = CONFIG_SETS["c1"]
