@@ -40,8 +40,8 @@ CONFIGS = {
     "c1": dict(name="FB_N1024_K512", n=1024, k=512, ebn0=2.5, frames=1 << 20, check=256),
     "c2": dict(name="frozen_n_4096_k_3072", n=4096, k=3072, ebn0=3.5, frames=1 << 20, check=256),
     "c3": dict(name="frozen_n_32768_k_29492_snr_4_5", n=32768, k=29492, ebn0=4.5, frames=1 << 17, check=64),
-    "c4": dict(name="frozen_n_131072_k_117964", n=131072, k=117964, ebn0=4.5, frames=1 << 15, check=16),
-    "c5": dict(name="frozen_n_524288_k_262144", n=524288, k=262144, ebn0=2.0, frames=1 << 14, check=4),
+    "c4": dict(name="frozen_n_131072_k_117964", n=131072, k=117964, ebn0=4.5, frames=1 << 16, check=16),
+    "c5": dict(name="frozen_n_524288_k_262144", n=524288, k=262144, ebn0=2.0, frames=1 << 15, check=4),
 }
 HEAD = "c2"
 CFG = dict(CONFIGS[HEAD], par=16, llr_bits=8)
