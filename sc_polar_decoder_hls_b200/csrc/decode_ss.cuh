@@ -531,10 +531,22 @@ struct SsThread {
     // task's plane buffer
     SS_DEV bool in_planes(uint32_t l, uint32_t wd) const { return wd == 0u && l >= p.lpre; }
     SS_DEV const uint4* asrc(uint32_t l, uint32_t wd) const { return in_planes(l, wd) ? pl + p.poff[l] : aptr(l); }
-    // partial sums of node level l, word w: component w & 3 of a quad
+    // partial sums of node level l, word w: component w & 3 of a quad.  The two bases are kept in registers and the
+    // choice is a select: as a branch with the base recomputed from the kernel parameters this helper alone was 15 % of
+    // the kernel's text and 5 % of its executed instructions
+    uint4* bsm;  // sm + p.sm_beta_off
+    uint4* bws;  // wsl + p.ws_beta_off
+    SS_DEV void bind(uint4* sm_, uint4* wsl_) {
+        sm = sm_;
+        wsl = wsl_;
+        bsm = sm_ + p.sm_beta_off;
+        bws = wsl_ + p.ws_beta_off;
+    }
     SS_DEV uint4* bquad(uint32_t l, uint32_t w) const {
-        if (l < p.lwin) return sm + p.sm_beta_off + (((w & (p.win_words - 1u)) >> 2) * 32u);
-        return wsl + p.ws_beta_off + ((w >> 2) * 32u);
+        const bool win = l < p.lwin;
+        uint4* base = win ? bsm : bws;
+        const uint32_t ww = win ? (w & (p.win_words - 1u)) : w;
+        return base + ((ww >> 2) * 32u);
     }
     SS_DEV uint32_t* bword(uint32_t l, uint32_t w) const { return reinterpret_cast<uint32_t*>(bquad(l, w)) + (w & 3u); }
 
@@ -974,7 +986,7 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     extern __shared__ __align__(16) uint4 ss_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     SsThread<Q, LOG2PAR, EXT, PROF> t(p);
-    t.sm = ss_smem + (size_t)warp * p.sm_stride + lane;
+    uint4* const sm_warp = ss_smem + (size_t)warp * p.sm_stride + lane;
     uint32_t* sm_sched = reinterpret_cast<uint32_t*>(ss_smem + (size_t)nwarps * p.sm_stride);
     // tensor memory for the alpha level p.ltm: warp w owns lanes 32 (w % 4) .. +31 (the only ones it can reach) and the
     // column range (w / 4) * tm_cols .. of the CTA's allocation
@@ -1006,7 +1018,7 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     }
     t.prof_on = PROF && p.prof != nullptr && warp == 0;
     const unsigned long long slot_id = (unsigned long long)blockIdx.x * nwarps + warp;
-    t.wsl = p.ws + slot_id * p.ws_stride + lane;
+    t.bind(sm_warp, p.ws + slot_id * p.ws_stride + lane);
     for (unsigned long long task = slot_id; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {
         t.pl = p.planes + task * p.planes_stride + lane;
         t.run();

@@ -105,8 +105,7 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     for (size_t task = 0; task < ntasks; task++) {
         for (int lane = 0; lane < 32; lane++) {
             SsThread<Q, LOG2PAR, EXT> t(p);
-            t.sm = smem.data() + lane;
-            t.wsl = ws.data() + lane;
+            t.bind(smem.data() + lane, ws.data() + lane);
             t.sched = sched.data();
             t.tm = tmem.data() + (size_t)lane * 512;
             t.pl = planes.data() + task * pl_stride + lane;
