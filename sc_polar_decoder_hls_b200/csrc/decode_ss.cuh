@@ -507,7 +507,7 @@ uint32_t ss_sub32(uint32_t s, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3
 }
 
 // One lane's view of the decoder state.  All pointers already include the lane.
-template <int Q, int LOG2PAR, bool EXT, bool PROF = false>
+template <int Q, int LOG2PAR, bool EXT, bool PROF = false, bool XF = false>
 struct SsThread {
     static constexpr int P = Q - 1;
     static constexpr int FMT = bs::FMT_CA2;
@@ -661,6 +661,43 @@ struct SsThread {
             op_x<G, false, true>(l, wd, zero);
         else
             op_x<G, false, false>(l, wd, zero);
+    }
+    // SS_XF_*: alpha[l-1] of the child = f / g of alpha[l], and alpha[l-2] = f of that child, in one pass: output chunk c of
+    // level l-2 needs chunks c and c + q of level l-1, i.e. chunks c, c + q, c + 2q, c + 3q of level l.  Both levels
+    // are stored (their g ops come later); alpha[l-1] is not read back.  All three levels are in global memory.
+    template <bool G>
+    SS_DEV void op_xf(uint32_t l, uint32_t wd, bool zero) {
+        const uint4* src = asrc(l, wd);
+        uint4* d1 = aptr(l - 1);
+        uint4* d2 = aptr(l - 2);
+        const uint32_t half = 1u << (l - 6), q = half >> 1;
+        const uint32_t* ub = (G && !zero) ? bword(l - 1, wd) : nullptr;
+        V a0, b0, a1, b1;
+        load_pair<false>(src, 0, half, a0, b0);
+        load_pair<false>(src, q, half, a1, b1);
+        for (uint32_t c = 0; c < q; c++) {
+            V r0, r1, r2;
+            uint32_t u0 = 0u, u1 = 0u;
+            if (G && !zero) {
+                u0 = ub[(c >> 2) * 128u + (c & 3u)];
+                u1 = ub[((c + q) >> 2) * 128u + ((c + q) & 3u)];
+            }
+            if constexpr (G) {
+                bs::g_sat_ca2<P>(a0, b0, u0, r0);
+                bs::g_sat_ca2<P>(a1, b1, u1, r1);
+            } else {
+                bs::f_op<P>(a0, b0, r0);
+                bs::f_op<P>(a1, b1, r1);
+            }
+            if (c + 1u < q) {  // the next unit's loads are in flight during the stores and the second-level f
+                load_pair<false>(src, c + 1u, half, a0, b0);
+                load_pair<false>(src, c + 1u + q, half, a1, b1);
+            }
+            store(d1 + c * 64u, r0);
+            store(d1 + (c + q) * 64u, r1);
+            bs::f_op<P>(r0, r1, r2);
+            store(d2 + c * 64u, r2);
+        }
     }
     // node (l, wd) := (left ^ right, right); copy: the left child is all-frozen      H_STATE my_module.h:903-932
     SS_DEV void op_h(uint32_t l, uint32_t wd, bool copy) {
@@ -825,7 +862,7 @@ struct SsThread {
                     atomicAdd(p.prof + 192u + prof_fn * 32u + prof_l, 1ull);
                 }
                 // rows: 0 F, 1 G (g and g0), 2 H, 3 R (64-LLR node incl. a fused level-7 op), 4 R0, 5 R1 (hard decision)
-                prof_fn = code == SS_F ? 0u : (code == SS_G || code == SS_G0) ? 1u : (code == SS_H || code == SS_HCOPY) ? 2u
+                prof_fn = (code == SS_F || code == SS_XF_F) ? 0u : (code == SS_G || code == SS_G0 || code == SS_XF_G || code == SS_XF_G0) ? 1u : (code == SS_H || code == SS_HCOPY) ? 2u
                           : (code == SS_SUB || code == SS_XS) ? 3u : code == SS_R0 ? 4u : code == SS_R1 ? 5u : 6u;
                 prof_l = (code == SS_SUB || code == SS_XS) ? 6u : l;
                 prof_t0 = clock64();
@@ -842,6 +879,19 @@ struct SsThread {
                     op_fg<true>(l, wd, code == SS_G0);
                     pc++;
                     break;
+                case SS_XF_F:
+                case SS_XF_G:
+                case SS_XF_G0:
+                    if constexpr (XF) {
+                        if (code == SS_XF_F)
+                            op_xf<false>(l, wd, false);
+                        else
+                            op_xf<true>(l, wd, code == SS_XF_G0);
+                        pc++;
+                        break;
+                    } else {
+                        return;  // a schedule with fused ops is never given to the lean kernel
+                    }
                 case SS_H:
                     op_h(l, wd, false);
                     pc++;
@@ -981,11 +1031,12 @@ __global__ void __launch_bounds__(256) ss_planes_kernel(const int8_t* __restrict
 #define SCPD_SS_THREADS 512  // upper bound of the CTA size: 16 warps, one CTA per SM, up to 128 registers
 #endif
 // PROF: the build with the per-stage clock64() histogram (scpd_stage_timing); the production kernel carries none of it
-template <int Q, int LOG2PAR, bool EXT, bool PROF = false>
+// XF: the build that also knows the fused SS_XF_* ops (large trees); the lean kernel of the small ones carries none of it
+template <int Q, int LOG2PAR, bool EXT, bool PROF = false, bool XF = false>
 __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const SsParams p) {
     extern __shared__ __align__(16) uint4 ss_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    SsThread<Q, LOG2PAR, EXT, PROF> t(p);
+    SsThread<Q, LOG2PAR, EXT, PROF, XF> t(p);
     uint4* const sm_warp = ss_smem + (size_t)warp * p.sm_stride + lane;
     uint32_t* sm_sched = reinterpret_cast<uint32_t*>(ss_smem + (size_t)nwarps * p.sm_stride);
     // tensor memory for the alpha level p.ltm: warp w owns lanes 32 (w % 4) .. +31 (the only ones it can reach) and the

@@ -160,6 +160,7 @@ struct scpd_decoder {
     size_t bs_planes_bytes = 0;
     // slot-sliced kernel plan (decode_ss.cuh): lane = frame; ss_ok == false: not available for this configuration
     int ss_pre = 0;  // leading f levels computed by the plane conversion
+    bool ss_xf = false;  // the schedule holds fused SS_XF_* ops (kernel instantiation with XF)
     bool ss_ok = false;
     int ss_warps = 16;
     int ss_max_log2n = 15;
@@ -293,8 +294,10 @@ static bs_kernel_t bs_kernel_ptr(int fmt, int q, int log2par, int ext, int g) {
 typedef void (*ss_kernel_t)(const SsParams);
 // Instantiated (LLR_BITS, log2 PAR, EXTENDED) combinations of the slot-sliced kernel (CA2 only).
 // prof: the instrumented build (scpd_stage_timing), instantiated for the BASELINE setting only
-static ss_kernel_t ss_kernel_ptr(int q, int log2par, int ext, bool prof = false) {
-    if (prof) return (q == 8 && log2par == 4 && ext == 1) ? sc_decode_ss_kernel<8, 4, true, true> : nullptr;
+static ss_kernel_t ss_kernel_ptr(int q, int log2par, int ext, bool prof = false, bool xf = false) {
+    // the instrumented build knows the fused ops as well (its code size does not matter)
+    if (prof) return (q == 8 && log2par == 4 && ext == 1) ? sc_decode_ss_kernel<8, 4, true, true, true> : nullptr;
+    if (xf) return (q == 8 && log2par == 4 && ext == 1) ? sc_decode_ss_kernel<8, 4, true, false, true> : nullptr;
 #define SS_K(Q, LP, E) \
     if (q == Q && log2par == LP && ext == (E ? 1 : 0)) return sc_decode_ss_kernel<Q, LP, E, false>;
     SS_K(8, 4, true)
@@ -340,9 +343,19 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
     // reads the planes once less), c1 362 -> 357 -> 349 (its level 9 would leave tensor memory): on from N = 2048
     d->ss_pre = ss_prefuse_depth(d->ss_sched_host, d->log2n, d->ss_plan.lsa,
                                  env_int("SCPD_SS_PRE", d->log2n >= 12 ? 2 : d->log2n == 11 ? 1 : 0));
-    d->ss_sched_host.erase(d->ss_sched_host.begin(), d->ss_sched_host.begin() + d->ss_pre);
+    // large trees (the walk is bound by DRAM): an f / g op whose result streams through global memory is fused with the f
+    // that opens the child, so that level is not read back (SS_XF_*, a separate instantiation of the kernel)
+    d->ss_xf = d->log2n >= env_int("SCPD_SS_XF_MIN_LOG2N", 15) && ss_kernel_ptr(q, d->log2par, (int)d->cfg.extended, false, true);
+    const int xf_min = d->ss_xf ? (int)std::max(d->ss_plan.lsa, d->ss_plan.ltm) + 1 : 0;
+    d->ss_sched_host = ss_build_schedule(d->log2n, (int)d->cfg.pruning, flags, &d->ss_stats, env_int("SCPD_SS_FUSE", 1), xf_min,
+                                         d->ss_pre);
+    if (d->ss_xf)
+        CUDA_TRY(cudaFuncSetAttribute((const void*)ss_kernel_ptr(q, d->log2par, (int)d->cfg.extended, false, true),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     d->ss_ok = true;
-    d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", 15);
+    // with the fused ops the slot-sliced kernel also wins on the largest trees (c4 275 vs 250, c5 101 vs 99 Gb/s); without
+    // that instantiation the frame-sliced kernel keeps N >= 2^16
+    d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", d->ss_xf ? 20 : 15);
     d->ss_min_tasks = (unsigned long long)env_int("SCPD_SS_MIN_TASKS", 4 * d->num_sms);
     if (env_int("SCPD_VERBOSE", 0))
         fprintf(stderr, "[scpd] slot-sliced kernel: %d warps/CTA, alpha levels 6..%u and partial sums below level %u in smem, "
@@ -902,7 +915,7 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     for (int s = 1; s <= d->ss_pre; s++) p.poff[d->log2n - s] = pre.off[s];
     p.prof = d->d_ss_prof;
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
-    ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->d_ss_prof != nullptr);
+    ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->d_ss_prof != nullptr, d->ss_xf);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
     k<<<dim3((unsigned)grid), dim3((unsigned)(warps * 32)), smem, st>>>(p);
     snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_ss_kernel (slot-sliced, lane per frame, %d warps/CTA)", warps);
@@ -958,9 +971,9 @@ extern "C" int scpd_decode(scpd_decoder* d, const int8_t* d_llr, size_t nframes,
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (d->raw_only) return decode_raw(d, d_llr, nframes, d_xhat, st);
-    // The slot-sliced kernel (a lane per frame) is the default for CA2 up to N = 2^15 once the batch gives every SM
-    // a few warps (measured, profiles/tuning_r2.md: 364 / 423 / 303 Gb/s against 231 / 288 / 287 at N = 1024 / 4096 /
-    // 32768; from N = 2^17 its 32-frame workspace per warp costs more DRAM traffic than the frame-sliced kernel's)
+    // The slot-sliced kernel (a lane per frame) is the default for CA2 once the batch gives every SM a few warps
+    // (measured, profiles/tuning_r2.md: 386 / 443 / 331 / 275 / 101 Gb/s against 231 / 288 / 287 / 250 / 99 at c1 ... c5);
+    // configurations without the instantiation that fuses f / g with the child's f use it up to N = 2^15
     if (d->ss_ok && (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0 &&
         (d->kernel_pinned || (d->log2n <= d->ss_max_log2n && (nframes + 31) / 32 >= d->ss_min_tasks)))
         return decode_ss(d, d_llr, nframes, d_xhat, st);

@@ -17,6 +17,9 @@
 //                           information flags; word 3 = pattern ids of the eight 8-LLR nodes, 4 bits each
 //   SS_XS + 4 words         SS_F / SS_G / SS_G0 at level 7 fused with the SS_SUB of the child it feeds: alpha[6]
 //                           stays in registers for the child's f (it is still stored for the child's g)
+//   SS_XF_F / _G / _G0      SS_F / SS_G / SS_G0 at level l fused with the SS_F(l-1) that opens the child: both levels are
+//                           written (the g ops need them), alpha[l-1] is not read back.  Only where the three levels
+//                           stream through global memory (large trees: the walk is bound by DRAM there)
 // Node types: 0 mixed, 1 all-frozen, 2 all-information; for nodes of 2 LLRs the code is the flag pair itself:
 // 0 = (0,1), 1 = (0,0), 2 = (1,1), 3 = (1,0).
 #pragma once
@@ -38,6 +41,9 @@ enum : uint32_t {
     SS_R1 = 7,
     SS_SUB = 8,
     SS_XS = 9,      // level-7 op (kind in bits [31:30] of the first descriptor word's upper bits, see below) + SUB
+    SS_XF_F = 10,   // SS_F / SS_G / SS_G0 at (l, o) + SS_F(l - 1) of the child it feeds
+    SS_XF_G = 11,
+    SS_XF_G0 = 12,
 };
 enum : uint32_t { SS_T_MIX = 0, SS_T_R0 = 1, SS_T_R1 = 2 };
 // information-flag patterns of 8-LLR nodes with a specialised routine (bit i = flag of position i); index = pattern
@@ -57,12 +63,14 @@ SS_HD static inline uint32_t ss_op_level(uint32_t w) { return (w >> 6) & 31u; }
 SS_HD static inline uint32_t ss_op_word(uint32_t w) { return (w >> 11) & 0xFFFFFu; }  // node offset / 32 = first partial-sum word
 
 struct SsStats {
-    uint64_t n_ops = 0, n_f = 0, n_g = 0, n_r0 = 0, n_r1 = 0, n_sub = 0, n_sub32_mixed = 0;
+    uint64_t n_ops = 0, n_f = 0, n_g = 0, n_r0 = 0, n_r1 = 0, n_sub = 0, n_sub32_mixed = 0, n_xf = 0;
 };
 
 struct SsBuilder {
     int log2n = 0, pruning = 0;
     int fuse = 1;  // 1: emit SS_XS for the level-7 op in front of a 64-LLR node
+    int xf_min = 0;  // > 0: fuse an f / g op at level l with the f that opens its child when l - 2 >= xf_min
+    int lead_skip = 0;  // the f ops of the leftmost nodes of the top lead_skip levels are computed by ss_planes_kernel
     const uint8_t* flags = nullptr;
     std::vector<uint32_t> psum;
     std::vector<uint32_t> ops;
@@ -139,9 +147,24 @@ struct SsBuilder {
             xs_done = true;
             return;
         }
+        // fused with the child's opening f: the child (l-1, oc) is a mixed node above the 64-LLR nodes whose left half is
+        // not all-frozen, i.e. emit() will start it with SS_F(l-1, oc) -- which skip_f then drops
+        if (xf_min > 0 && l - 2 >= xf_min && l - 2 >= 7 && !in_r1) {
+            const uint32_t cc = count(oc, h);
+            const bool mixed = !(pruning >= 1 && cc == 0) && !(pruning >= 2 && cc == h);
+            if (mixed && !(pruning >= 1 && count(oc, h >> 1) == 0)) {
+                ops.push_back(ss_op_make(kind == SS_F ? SS_XF_F : kind == SS_G ? SS_XF_G : SS_XF_G0, l, o));
+                st.n_f += h >> 1;
+                st.n_xf++;
+                skip_f = true;
+                return;
+            }
+        }
         ops.push_back(ss_op_make(kind, l, o));
     }
     bool xs_done = false;
+    bool skip_f = false;  // the next emit() finds its opening f already done by an SS_XF_* op
+    bool in_r1 = false;   // inside the plain-SC walk behind an SS_R1 (not fused: the exception path stays simple)
 
     void emit_child(int l, uint32_t o, bool r1) {
         if (xs_done) {  // the SS_XS in front already decoded this 64-LLR node
@@ -167,11 +190,14 @@ struct SsBuilder {
         const uint32_t h = 1u << (l - 1);
         // work counters: the fallback is the exception, do not count it
         const SsStats keep = st;
+        const bool was = in_r1;
+        in_r1 = true;
         emit_x(SS_F, l, o, o);
         emit_child(l - 1, o, true);
         emit_x(SS_G, l, o, o + h);
         emit_child(l - 1, o + h, true);
         ops.push_back(ss_op_make(SS_H, l, o));
+        in_r1 = was;
         st = keep;
         ops[at] = (uint32_t)(ops.size() - at - 1);
     }
@@ -200,7 +226,12 @@ struct SsBuilder {
             ops.push_back(ss_op_make(SS_HCOPY, l, o));
             return;
         }
-        emit_x(SS_F, l, o, o);
+        if (skip_f)
+            skip_f = false;  // done by the SS_XF_* op of the parent
+        else if (o == 0 && l > log2n - lead_skip && !in_r1)
+            st.n_f += h;     // done by the plane conversion (ss_prefuse_depth)
+        else
+            emit_x(SS_F, l, o, o);
         emit_child(l - 1, o, false);
         if (right_r0) {
             ops.push_back(ss_op_make(SS_R0, l - 1, o + h));
@@ -216,11 +247,13 @@ struct SsBuilder {
 
 // flags: n bytes, 1 = information bit; log2n >= 7.  pruning: 0 none, 1 all-frozen nodes, 2 + all-information nodes.
 static inline std::vector<uint32_t> ss_build_schedule(int log2n, int pruning, const uint8_t* flags, SsStats* stats,
-                                                      int fuse = 1) {
+                                                      int fuse = 1, int xf_min = 0, int lead_skip = 0) {
     SsBuilder b;
     b.log2n = log2n;
     b.pruning = pruning;
     b.fuse = fuse;
+    b.xf_min = xf_min;
+    b.lead_skip = lead_skip;
     b.flags = flags;
     const uint32_t n = 1u << log2n;
     b.psum.assign(n + 1, 0);
@@ -260,8 +293,9 @@ static inline size_t ss_planes_quads(int log2n, int pre = 0, uint32_t* off = nul
     }
     return q;
 }
-// How many leading ops of the schedule are F(log2n, 0), F(log2n - 1, 0), ... whose result neither lives on chip (level
-// above lsa) nor is smaller than a unit of the plane kernel: those are stripped and computed by ss_planes_kernel.
+// How many leading ops of the schedule (built without fused ops and with lead_skip = 0) are F(log2n, 0), F(log2n - 1, 0),
+// ... whose result neither lives on chip (level above lsa) nor is smaller than a unit of the plane kernel: those are
+// computed by ss_planes_kernel; the schedule is then built again with lead_skip = that depth.
 static inline int ss_prefuse_depth(const std::vector<uint32_t>& ops, int log2n, uint32_t lsa, int max_depth) {
     int d = 0;
     while (d < max_depth && d < 3 && (size_t)d < ops.size() && ss_op_code(ops[d]) == SS_F && (int)ss_op_level(ops[d]) == log2n - d &&

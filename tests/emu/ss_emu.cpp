@@ -25,7 +25,7 @@ using namespace scpd;
 
 template <int Q, int LOG2PAR, bool EXT>
 static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, size_t nframes, uint32_t* xhat,
-               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats, int ltm, int max_pre) {
+               size_t smem_per_warp, int force_lsa, int force_lwin, int fuse, uint64_t* stats, int ltm, int max_pre, int xf) {
     constexpr int P = Q - 1;
     const uint32_t n = 1u << log2n;
     SsStats st;
@@ -42,8 +42,12 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     const size_t ntasks = (nframes + 31) / 32;
     // the leading f ops are computed with the planes (scpd_api.cu: plan_ss / decode_ss)
     const int pre = ss_prefuse_depth(sched, log2n, plan.lsa, max_pre);
-    sched.erase(sched.begin(), sched.begin() + pre);
-    if (stats) stats[4] = (uint64_t)pre;
+    // xf: fused SS_XF_* ops wherever the three levels involved live in global memory (scpd_api.cu: large trees only)
+    sched = ss_build_schedule(log2n, pruning, flags, &st, fuse, xf ? (int)std::max(plan.lsa, plan.ltm) + 1 : 0, pre);
+    if (stats) {
+        stats[4] = (uint64_t)pre;
+        stats[5] = st.n_xf;
+    }
     SsPre pre_off;
     const size_t pl_stride = ss_planes_quads(log2n, pre, pre_off.off);
     std::vector<uint4> planes(ntasks * pl_stride, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
@@ -104,7 +108,7 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     std::vector<uint32_t> tmem((size_t)32 * 512, 0xDEADBEEFu);  // 512 columns per lane
     for (size_t task = 0; task < ntasks; task++) {
         for (int lane = 0; lane < 32; lane++) {
-            SsThread<Q, LOG2PAR, EXT> t(p);
+            SsThread<Q, LOG2PAR, EXT, false, true> t(p);
             t.bind(smem.data() + lane, ws.data() + lane);
             t.sched = sched.data();
             t.tm = tmem.data() + (size_t)lane * 512;
@@ -118,10 +122,10 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
 
 extern "C" int ss_emu_decode(int log2n, int q, int log2par, int ext, int pruning, const uint8_t* flags, const int8_t* llr,
                              size_t nframes, uint32_t* xhat, size_t smem_per_warp, int force_lsa, int force_lwin, int fuse,
-                             uint64_t* stats, int ltm, int max_pre) {
+                             uint64_t* stats, int ltm, int max_pre, int xf) {
 #define SS_CASE(Q, LP, E)                          \
     if (q == Q && log2par == LP && ext == (E ? 1 : 0)) \
-        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats, ltm, max_pre);
+        return run<Q, LP, E>(log2n, pruning, flags, llr, nframes, xhat, smem_per_warp, force_lsa, force_lwin, fuse, stats, ltm, max_pre, xf);
     SS_CASE(8, 4, true)
     SS_CASE(8, 4, false)
     SS_CASE(6, 4, true)

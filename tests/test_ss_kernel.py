@@ -13,13 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = {}
 
 
-def ss_emu(flags, n, par, q, ext, prune, llr, smem=18 * 1024, lsa=-1, lwin=-1, fuse=1, ltm=0, pre=2):
+def ss_emu(flags, n, par, q, ext, prune, llr, smem=18 * 1024, lsa=-1, lwin=-1, fuse=1, ltm=0, pre=2, xf=0):
     if "l" not in _LIB:
         _LIB["l"] = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libss_emu.so"))
     out = np.zeros((len(llr), n // 32), np.uint32)
-    st = (ctypes.c_uint64 * 5)()
+    st = (ctypes.c_uint64 * 6)()
     rc = _LIB["l"].ss_emu_decode(int(np.log2(n)), q, int(np.log2(par)), ext, prune, ol.P(flags), ol.P(llr),
-                                 ctypes.c_size_t(len(llr)), ol.P(out), ctypes.c_size_t(smem), lsa, lwin, fuse, st, ltm, pre)
+                                 ctypes.c_size_t(len(llr)), ol.P(out), ctypes.c_size_t(smem), lsa, lwin, fuse, st, ltm, pre, xf)
     assert rc == 0, rc
     return out, [int(v) for v in st]
 
@@ -112,3 +112,21 @@ def test_ss_leading_f_levels_computed_with_the_planes(name, n, k):
     assert st[4] == 0 and (got == ol.decode_packed(n, 16, 8, 0, 1, half, llr)).all()
     got, st = ss_emu(np.ones(n, np.uint8), n, 16, 8, 1, 2, llr, pre=3)   # all-information root: hard decision first
     assert st[4] == 0 and (got == ol.decode_packed(n, 16, 8, 0, 1, np.ones(n, np.uint8), llr)).all()
+
+
+@pytest.mark.parametrize("lsa,ltm,pre", [(6, 0, 0), (7, 0, 2), (7, 9, 2), (6, 8, 1), (8, 0, 3)])
+def test_ss_fused_f_g_with_the_childs_opening_f(lsa, ltm, pre):
+    """SS_XF_*: an f / g op fused with the f that opens its child (both levels written, the middle one not read back), used
+    for large trees where those levels stream through DRAM; here forced onto c2 so that it runs wherever the three levels
+    live in global memory, in every pruning mode, with zero LLRs (the fallback walk behind an R1 op is never fused) and
+    together with the levels computed by the plane conversion."""
+    name, n, k = "frozen_n_4096_k_3072", 4096, 3072
+    flags = scpd.packed_flags(name, n)
+    llr = _llrs(np.random.default_rng(lsa * 10 + ltm), n, k, 8, nfr=6)
+    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
+    for prune in (0, 1, 2):
+        got, st = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=64 * 1024, lsa=lsa, lwin=8, ltm=ltm, pre=pre, xf=1)
+        assert (got == want).all(), prune
+        assert st[5] > 0
+    got, st = ss_emu(flags, n, 16, 8, 1, 2, llr, smem=64 * 1024, lsa=lsa, lwin=8, ltm=ltm, pre=pre, xf=0)
+    assert (got == want).all() and st[5] == 0
