@@ -356,7 +356,8 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
     // with the fused ops the slot-sliced kernel also wins on the largest trees (c4 275 vs 250, c5 101 vs 99 Gb/s); without
     // that instantiation the frame-sliced kernel keeps N >= 2^16
     d->ss_max_log2n = env_int("SCPD_SS_MAX_LOG2N", d->ss_xf ? 20 : 15);
-    d->ss_min_tasks = (unsigned long long)env_int("SCPD_SS_MIN_TASKS", 4 * d->num_sms);
+    // measured crossover with the int16x2 kernel (tools/r2_small.sh): between 8192 and 12288 frames at c1, c2 and c3
+    d->ss_min_tasks = (unsigned long long)env_int("SCPD_SS_MIN_TASKS", 5 * d->num_sms / 2);
     if (env_int("SCPD_VERBOSE", 0))
         fprintf(stderr, "[scpd] slot-sliced kernel: %d warps/CTA, alpha levels 6..%u and partial sums below level %u in smem, "
                 "%u B/warp, alpha level %u in tensor memory (%u columns/warp), workspace %llu B/warp, %zu schedule words (%s)\n",
