@@ -396,6 +396,38 @@ def test_slot_sliced_kernel_edge_cases(scpd, monkeypatch):
             dec.close()
 
 
+@pytest.mark.parametrize("n,xf_min,pre", [(4096, 12, 2), (4096, 12, 0), (8192, 13, 3), (32768, 15, 2), (32768, 99, 1), (65536, 15, 2)])
+def test_slot_sliced_large_tree_ops_on_arbitrary_tables(scpd, monkeypatch, n, xf_min, pre):
+    """The two things the slot-sliced kernel does beyond the plain schedule -- the leading f levels computed by the plane
+    conversion (SCPD_SS_PRE) and f / g fused with the child's opening f (SS_XF_*, forced onto small trees here) -- on
+    flag tables no construction produces: random densities, an all-frozen first half or quarter (no leading f), an
+    all-information second half (R1 with its fallback walk), every pruning mode, LLRs with many CA2 zeros, ragged batch."""
+    monkeypatch.setenv("SCPD_KERNEL", "ss")
+    monkeypatch.setenv("SCPD_SS_XF_MIN_LOG2N", str(xf_min))
+    monkeypatch.setenv("SCPD_SS_PRE", str(pre))
+    rng = np.random.default_rng(n + xf_min + pre)
+    nfr = 37 if n <= 8192 else 33
+    for trial in range(4):
+        dens = rng.random(n // 256).repeat(256)              # blocks of 256 positions with their own density
+        flags = (rng.random(n) < dens).astype(np.uint8)
+        if trial == 1:
+            flags[:n // 2] = 0
+        if trial == 2:
+            flags[:n // 4] = 0
+            flags[n // 2:] = 1
+        if trial == 3:
+            flags[n // 8:n // 4] = 1
+        llr = rng.integers(-127, 128, size=(nfr, n)).astype(np.int8)
+        llr[rng.random(llr.shape) < 0.2] = 0
+        llr[0] = 0
+        want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr, threads=8)
+        for prune in (0, 1, 2):
+            dec = scpd.Decoder(n, int(flags.sum()), flags, par=16, pruning=prune)
+            assert "slot-sliced" in dec.kernel_name
+            assert (dec.decode_host(llr) == want).all(), (trial, prune)
+            dec.close()
+
+
 def test_slot_sliced_is_the_default_for_large_batches(scpd):
     """scpd_decode's kernel choice for CA2 up to N = 2^14: the slot-sliced kernel once the batch gives every SM a few
     warps, the int16x2 kernel below -- and the same bits whichever kernel runs."""
