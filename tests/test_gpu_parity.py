@@ -65,7 +65,7 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
 
 
 @pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "coop4", "coop8", "bs8", "bs16", "bs32", "bs32ws",
-                        "ss", "ss12", "ss_notm", "ss_tm8", "ss_nofuse"])
+                        "ss", "ss12", "ss_notm", "ss_tm8", "ss_nofuse", "ss_xf", "ss_pre0", "ss_pre3"])
 def kernel_mode(request, monkeypatch):
     """Selects the decode kernel through the library's environment switches (read in scpd_create):
     the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
@@ -73,7 +73,7 @@ def kernel_mode(request, monkeypatch):
     generic kernel, the raw-pattern kernel, and the library's own choice."""
     mode = request.param
     for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_COOP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS", "SCPD_SS_WARPS",
-              "SCPD_SS_LTM", "SCPD_SS_LSA", "SCPD_SS_LWIN", "SCPD_SS_FUSE"):
+              "SCPD_SS_LTM", "SCPD_SS_LSA", "SCPD_SS_LWIN", "SCPD_SS_FUSE", "SCPD_SS_XF_MIN_LOG2N", "SCPD_SS_PRE"):
         monkeypatch.delenv(v, raising=False)
     if mode.startswith("ss"):
         # the slot-sliced kernel (a lane per frame): default plan (16 warps per CTA, one LLR level in tensor memory),
@@ -89,6 +89,12 @@ def kernel_mode(request, monkeypatch):
             monkeypatch.setenv("SCPD_SS_LWIN", "8")
         elif mode == "ss_nofuse":
             monkeypatch.setenv("SCPD_SS_FUSE", "0")
+        elif mode == "ss_xf":      # f / g fused with the child's opening f wherever three levels stream through global memory
+            monkeypatch.setenv("SCPD_SS_XF_MIN_LOG2N", "10")
+        elif mode == "ss_pre0":    # every f level computed by the walk
+            monkeypatch.setenv("SCPD_SS_PRE", "0")
+        elif mode == "ss_pre3":    # as many leading f levels as the plane conversion can take
+            monkeypatch.setenv("SCPD_SS_PRE", "3")
         return mode
     if mode in ("generic", "raw"):
         monkeypatch.setenv("SCPD_KERNEL", mode)
@@ -110,7 +116,7 @@ def kernel_mode(request, monkeypatch):
 @pytest.mark.parametrize("key,nfr", [("c1", 600), ("c2", 150), ("c3", 8)])
 @pytest.mark.parametrize("prune", [0, 1, 2])
 def test_every_kernel_variant(scpd, kernel_mode, key, nfr, prune):
-    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8", "coop4", "ss", "ss_tm8"):
+    if key == "c3" and kernel_mode not in ("auto", "bs32", "bs32ws", "fast8", "coop4", "ss", "ss_tm8", "ss_xf", "ss_pre3"):
         pytest.skip("the large tree is covered by one variant per kernel family")
     name, n, k, snr = CONFIG_SETS[key]
     llr = _llrs(21, n, nfr, k, snr).copy()
