@@ -89,10 +89,14 @@ __device__ __forceinline__ int quantize_llr(float y) {  // sc_quantizer.h:77-80 
 // further than 2.5e-4 max(sigma, 1) from a bin edge of the quantiser has its bin decided; the others (and r1 > 0.999, where
 // the relative error of log explodes) are recomputed with the libm-grade code: same LLRs, about half the instructions.
 // fast = 1: approximations only (a quantised LLR differs by one step on about 1e-5 of the samples).
+// FAST (the mode above) and CW (a codeword is given; otherwise all-zero: every symbol +1) are compile-time: the kernel is
+// bound by instruction issue, and the per-draw tests of run-time flags were a tenth of its instructions.
+template <int FAST, bool CW>
 __global__ void __launch_bounds__(128)
 channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nframes, uint32_t seed, float sigma,
                const uint8_t* __restrict__ codeword, int per_frame, int8_t* __restrict__ llr, XsJumpTable jt, int log2c,
-               uint32_t fpb /* frames per block */, int fast) {
+               uint32_t fpb /* frames per block */) {
+    constexpr int fast = FAST;
     const int lane = threadIdx.x & 31;
     const unsigned long long blk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned long long f0 = blk * fpb;
@@ -124,15 +128,13 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
     const float guard = 2.5e-4f * fmaxf(sigma, 1.0f);
     const uint32_t nmask = n - 1u;
     const bool aligned = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
-    // 16 bytes (8 draws) per store; a lane's range is a multiple of 16 bytes for every n >= 2 ... when 2c >= 16,
-    // shorter ranges (2c = 2, 4, 8: blocks of fewer than 256 bytes) store byte pairs
-    const uint32_t per = c >= 8 ? 8u : (uint32_t)c;
+    // 16 bytes (8 draws) per store: a block is 32768 LLRs or one frame of more than that, so c >= 512 (the host checks)
+    constexpr uint32_t per = 8u;
     for (unsigned long long d = 0; d < c; d += per) {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         const unsigned long long i0 = byte0 + 2ull * d;  // byte offset inside the block
 #pragma unroll
         for (uint32_t k = 0; k < 8; k++) {
-            if (k >= per) break;
             float r1 = xs128_uniform(xs128_next(a));
             float r2 = xs128_uniform(xs128_next(b));
             r1 = fmaxf(r1, 5.9604644775390625e-08f);  // the reference has UB at r1 == 0
@@ -146,9 +148,9 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
                 x = sqrtf(__fmul_rn(-2.0f, logf(r1)));  // :68
                 sincosf(y, &sn, &cs);
             }
-            float ph = __fmul_rn(x, sn), qu = __fmul_rn(x, cs);  // :74-77
+            const float ph = __fmul_rn(x, sn), qu = __fmul_rn(x, cs);  // :74-77
             float s0 = 1.0f, s1 = 1.0f;  // sc_bpsk.h:53
-            if (codeword) {
+            if (CW) {
                 const unsigned long long i = i0 + 2u * k;
                 const uint32_t pos = (uint32_t)i & nmask;
                 if (per_frame == 2) {  // packed rows [frame][n / 32] (the reference words scpd_run_ber_ex builds on the device)
@@ -162,24 +164,27 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
                     s1 = cw[pos + 1] ? -1.0f : 1.0f;
                 }
             }
+            float v0 = __fadd_rn(s0, __fmul_rn(ph, sigma)), v1 = __fadd_rn(s1, __fmul_rn(qu, sigma));  // sc_adder.h:139-140
             if (fast == 2) {  // guarded: is the quantiser bin of both samples decided whatever the approximation error?
-                const float t0 = __fmul_rn(__fadd_rn(s0, __fmul_rn(ph, sigma)), 4.0f);
-                const float t1 = __fmul_rn(__fadd_rn(s1, __fmul_rn(qu, sigma)), 4.0f);
-                const bool edge0 = fabsf(t0 - rintf(t0)) < guard && fabsf(t0) < 33.0f;
-                const bool edge1 = fabsf(t1 - rintf(t1)) < guard && fabsf(t1) < 33.0f;
-                if (edge0 || edge1 || !(r1 <= 0.999f)) {
+                // distance to the nearest integer through the 1.5 * 2^23 trick (|t| < 2^22: two FADDs on the FMA pipe
+                // instead of an FRND on the conversion pipe, which this kernel keeps almost as busy as the issue slots)
+                const float t0 = __fmul_rn(v0, 4.0f), t1 = __fmul_rn(v1, 4.0f);
+                const float n0 = __fsub_rn(__fadd_rn(t0, 12582912.0f), 12582912.0f);
+                const float n1 = __fsub_rn(__fadd_rn(t1, 12582912.0f), 12582912.0f);
+                const float dist = fminf(fabsf(__fsub_rn(t0, n0)), fabsf(__fsub_rn(t1, n1)));
+                if (dist < guard || !(r1 <= 0.999f)) {
                     x = sqrtf(__fmul_rn(-2.0f, logf(r1)));
                     sincosf(y, &sn, &cs);
-                    ph = __fmul_rn(x, sn);
-                    qu = __fmul_rn(x, cs);
+                    v0 = __fadd_rn(s0, __fmul_rn(__fmul_rn(x, sn), sigma));
+                    v1 = __fadd_rn(s1, __fmul_rn(__fmul_rn(x, cs), sigma));
                 }
             }
-            const int q0 = quantize_llr(__fadd_rn(s0, __fmul_rn(ph, sigma)));  // sc_adder.h:139-140
-            const int q1 = quantize_llr(__fadd_rn(s1, __fmul_rn(qu, sigma)));
+            const int q0 = quantize_llr(v0);
+            const int q1 = quantize_llr(v1);
             w[k >> 1] |= (((uint32_t)q0 & 0xFFu) | (((uint32_t)q1 & 0xFFu) << 8)) << (16 * (k & 1));
         }
         if (i0 < valid) {
-            if (per == 8u && aligned && i0 + 16u <= valid) {
+            if (aligned && i0 + 16u <= valid) {
                 *reinterpret_cast<uint4*>(out + i0) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {  // short lane ranges (n < 16 at the end of the batch) or a buffer that is not 16-byte aligned
                 for (uint32_t k = 0; k < per; k++)

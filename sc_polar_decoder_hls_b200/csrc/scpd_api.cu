@@ -1268,11 +1268,18 @@ extern "C" int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nf
     if (rc) return rc;
     // a warp per block of frames: 32768 LLRs when the frame is shorter than that (harness.cuh)
     const uint32_t fpb = n < 32768u ? 32768u / n : 1u;
-    const int log2c = ilog2(fpb * n / 64u);
+    const int log2c = ilog2(fpb * n / 64u);  // >= 9: a lane's range is a whole number of 16-byte stores
     const unsigned long long nblk = (nframes + fpb - 1) / fpb;
     const unsigned grid = (unsigned)((nblk + 3) / 4);
-    channel_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, d_codeword, per_frame,
-                                                           d_llr, jt, log2c, fpb, channel_mode().load());
+    const int mode = channel_mode().load();
+#define SCPD_CHAN(M, C) \
+    channel_kernel<M, C><<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, d_codeword, per_frame, d_llr, jt, log2c, fpb)
+    if (d_codeword) {
+        if (mode == 0) SCPD_CHAN(0, true); else if (mode == 1) SCPD_CHAN(1, true); else SCPD_CHAN(2, true);
+    } else {
+        if (mode == 0) SCPD_CHAN(0, false); else if (mode == 1) SCPD_CHAN(1, false); else SCPD_CHAN(2, false);
+    }
+#undef SCPD_CHAN
     CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
 }
