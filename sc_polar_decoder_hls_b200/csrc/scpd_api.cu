@@ -159,6 +159,7 @@ struct scpd_decoder {
     uint8_t* d_bs_planes = nullptr;
     size_t bs_planes_bytes = 0;
     // slot-sliced kernel plan (decode_ss.cuh): lane = frame; ss_ok == false: not available for this configuration
+    int ber_batch_mb = 2048;  // LLR staging per batch of the Monte-Carlo loop
     int ss_pre = 0;  // leading f levels computed by the plane conversion
     bool ss_xf = false;  // the schedule holds fused SS_XF_* ops (kernel instantiation with XF)
     bool ss_ok = false;
@@ -645,6 +646,7 @@ extern "C" int scpd_create(const scpd_config* cfg, const uint8_t* flags, int dev
     d->bs_prefetch = (uint32_t)env_int("SCPD_BS_PREFETCH", d->log2n <= 11 ? 1 : 0);
     d->bs_min_groups = (unsigned long long)env_int("SCPD_BS_MIN_GROUPS", d->log2n <= 11 ? 1536 : d->log2n <= 13 ? 768 : d->log2n <= 17 ? 512 : 256);
     d->host_chunk_mb = (size_t)env_int("SCPD_HOST_CHUNK_MB", 256);
+    d->ber_batch_mb = std::max(1, env_int("SCPD_BER_BATCH_MB", 2048));
     d->raw_only = raw_only;
     int rc = SCPD_OK;
     if (!raw_only) {
@@ -1322,10 +1324,15 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
     CUDA_TRY(cudaSetDevice(d->device));
     const uint32_t n = d->cfg.n, wpf = d->wpf;
     std::memset(h_counters, 0, 10 * sizeof(uint64_t));
-    // batch so that LLR staging stays around 0.5 GiB per buffer, but never fewer than 8 tasks of 32 frames per SM
-    size_t batch = (size_t)((1ull << 29) / n);
+    // batch so that LLR staging stays around 2 GiB per buffer, but never fewer than 8 tasks of 32 frames per SM; a whole
+    // number of rounds of the slot-sliced kernel's resident warps, so that no decode of the loop ends on a ragged round
+    size_t batch = (size_t)(((size_t)d->ber_batch_mb << 20) / n);
     batch = std::max<size_t>(batch, (size_t)8 * 32 * (size_t)d->num_sms);
     batch &= ~(size_t)31;
+    if (d->ss_ok && d->log2n <= d->ss_max_log2n) {
+        const size_t round = (size_t)d->num_sms * (size_t)d->ss_warps * 32;
+        if (batch >= round) batch = batch / round * round;
+    }
     if (batch > nframes) batch = (size_t)nframes;
     if (batch == 0) return SCPD_OK;
     int rc = ensure_pipeline(d, batch);
