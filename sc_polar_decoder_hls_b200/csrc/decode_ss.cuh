@@ -536,9 +536,11 @@ struct SsThread {
     // the kernel's text and 5 % of its executed instructions
     uint4* bsm;  // sm + p.sm_beta_off
     uint4* bws;  // wsl + p.ws_beta_off
+    uint4* a6;   // alpha[6]: always in shared memory, touched by every 64-LLR node
     SS_DEV void bind(uint4* sm_, uint4* wsl_) {
         sm = sm_;
         wsl = wsl_;
+        a6 = sm_ + p.aoff[6];
         bsm = sm_ + p.sm_beta_off;
         bws = wsl_ + p.ws_beta_off;
     }
@@ -793,8 +795,8 @@ struct SsThread {
         }
         if (walk) {
             if (!stored && tr != SS_T_R0 && tl != SS_T_R0) {
-                store(aptr(6), a);
-                store(aptr(6) + 64, b);
+                store(a6, a);
+                store(a6 + 64, b);
             }
             if (tl != SS_T_R0) {
                 V r;
@@ -805,8 +807,8 @@ struct SsThread {
                 V r;
                 if (tl != SS_T_R0) {
                     V a2, b2;  // reloaded: keeping 16 registers alive across the left child costs more
-                    load(aptr(6), a2);
-                    load(aptr(6) + 64, b2);
+                    load(a6, a2);
+                    load(a6 + 64, b2);
                     bs::g_sat_ca2<P>(a2, b2, bl, r);
                 } else {
                     bs::g_sat_ca2<P>(a, b, 0u, r);
@@ -821,8 +823,8 @@ struct SsThread {
         const uint32_t d0 = sched[pc + 1], kind = (d0 >> 8) & 3u;
         V r0, r1;
         if (!xs) {
-            load(aptr(6), r0);
-            load(aptr(6) + 64, r1);
+            load(a6, r0);
+            load(a6 + 64, r1);
         } else {
             const uint4* src = asrc(7, wd & ~3u);  // N = 128: the root
             V a0, b0, a1, b1;
