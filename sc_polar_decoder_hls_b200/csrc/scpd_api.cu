@@ -298,7 +298,15 @@ typedef void (*ss_kernel_t)(const SsParams);
 static ss_kernel_t ss_kernel_ptr(int q, int log2par, int ext, bool prof = false, bool xf = false) {
     // the instrumented build knows the fused ops as well (its code size does not matter)
     if (prof) return (q == 8 && log2par == 4 && ext == 1) ? sc_decode_ss_kernel<8, 4, true, true, true> : nullptr;
-    if (xf) return (q == 8 && log2par == 4 && ext == 1) ? sc_decode_ss_kernel<8, 4, true, false, true> : nullptr;
+    if (xf) {  // the build with the fused SS_XF_* ops (large trees)
+        if (q == 8 && log2par == 4 && ext == 1) return sc_decode_ss_kernel<8, 4, true, false, true>;
+#ifndef SCPD_FAST_BUILD
+        if (q == 8 && log2par == 4 && ext == 0) return sc_decode_ss_kernel<8, 4, false, false, true>;
+        if (q == 7 && log2par == 4 && ext == 1) return sc_decode_ss_kernel<7, 4, true, false, true>;
+        if (q == 6 && log2par == 4 && ext == 1) return sc_decode_ss_kernel<6, 4, true, false, true>;
+#endif
+        return nullptr;
+    }
 #define SS_K(Q, LP, E) \
     if (q == Q && log2par == LP && ext == (E ? 1 : 0)) return sc_decode_ss_kernel<Q, LP, E, false>;
     SS_K(8, 4, true)

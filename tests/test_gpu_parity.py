@@ -434,6 +434,28 @@ def test_slot_sliced_large_tree_ops_on_arbitrary_tables(scpd, monkeypatch, n, xf
             dec.close()
 
 
+@pytest.mark.parametrize("q,ext", [(8, 0), (7, 1), (6, 1)])
+def test_slot_sliced_fused_ops_other_configurations(scpd, monkeypatch, q, ext):
+    """The instantiations of the kernel with the fused SS_XF_* ops other than the headline one (LLR_BITS 6 / 7, EXTENDED 0),
+    forced onto c2 and used by default at c3; full internal range of the saturation, zeros, every pruning mode."""
+    monkeypatch.setenv("SCPD_KERNEL", "ss")
+    rng = np.random.default_rng(q * 2 + ext)
+    ma = (1 << (q - 1)) - 1
+    for key, nfr, xf_min in (("c2", 70, "12"), ("c3", 6, "15")):
+        monkeypatch.setenv("SCPD_SS_XF_MIN_LOG2N", xf_min)
+        name, n, k, snr = CONFIG_SETS[key]
+        flags = scpd.packed_flags(name, n)
+        llr = ol.test_llrs(rng, n, nfr, k, snr, maxabs=min(31, ma))
+        llr[nfr // 2:] = rng.integers(-ma, ma + 1, size=(nfr - nfr // 2, n))
+        llr[-1][::3] = 0
+        want = ol.decode_packed(n, 16, q, 0, ext, flags, llr, threads=8)
+        for prune in (0, 2):
+            dec = scpd.Decoder(n, k, flags, par=16, llr_bits=q, extended=ext, pruning=prune)
+            assert "slot-sliced" in dec.kernel_name
+            assert (dec.decode_host(llr) == want).all(), (key, prune)
+            dec.close()
+
+
 def test_slot_sliced_is_the_default_for_large_batches(scpd):
     """scpd_decode's kernel choice for CA2 up to N = 2^14: the slot-sliced kernel once the batch gives every SM a few
     warps, the int16x2 kernel below -- and the same bits whichever kernel runs."""
