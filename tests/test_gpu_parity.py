@@ -456,6 +456,23 @@ def test_slot_sliced_fused_ops_other_configurations(scpd, monkeypatch, q, ext):
             dec.close()
 
 
+@pytest.mark.parametrize("key,nfr", [("c4", 40), ("c5", 9)])
+def test_slot_sliced_kernel_on_the_largest_trees(scpd, monkeypatch, key, nfr):
+    """c4 / c5 on the slot-sliced kernel with its fused ops (what scpd_decode launches for large batches of them; pinned
+    here because the oracle needs a second per frame of N = 2^19): channel frames, zero-heavy frames, ragged task."""
+    monkeypatch.setenv("SCPD_KERNEL", "ss")
+    name, n, k, snr = CONFIG_SETS[key]
+    flags = scpd.packed_flags(name, n)
+    llr = _llrs(5, n, nfr, k, snr).copy()
+    llr[-1] = 0
+    llr[-2][::5] = 0
+    dec = scpd.Decoder(n, k, flags)
+    got = dec.decode_host(llr)
+    assert "slot-sliced" in dec.last_kernel_name
+    assert (got == _oracle(n, 16, 8, 1, flags, llr)).all()
+    dec.close()
+
+
 def test_slot_sliced_is_the_default_for_large_batches(scpd):
     """scpd_decode's kernel choice for CA2 up to N = 2^14: the slot-sliced kernel once the batch gives every SM a few
     warps, the int16x2 kernel below -- and the same bits whichever kernel runs."""
