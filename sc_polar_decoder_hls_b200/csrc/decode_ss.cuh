@@ -78,6 +78,9 @@ struct SsParams {
     // lpre = log2n: nothing prefused) and the walk starts below it
     uint32_t lpre;
     uint32_t poff[24];
+    // alpha[lhot] (the smallest workspace level) in its own dense array: hot + slot * hot_stride; lhot = 0: none
+    uint4* hot;
+    uint32_t lhot, hot_stride;
     // != nullptr: per (function, level) SM-clock cycles [6][32] and visits [6][32] of warp 0 of every CTA (scpd_stage_time)
     unsigned long long* prof;
 };
@@ -525,7 +528,7 @@ struct SsThread {
     SS_DEV SsThread(const SsParams& p_) : p(p_) {}
 
     SS_DEV uint4* aptr(uint32_t l) const {  // not for l == p.ltm (tensor memory)
-        return (l <= p.lsa ? sm : wsl) + p.aoff[l];
+        return (l <= p.lsa ? sm : l == p.lhot ? wsh : wsl) + p.aoff[l];
     }
     // alpha[l] of the node whose first partial-sum word is wd: the root and the prefused leftmost nodes come from the
     // task's plane buffer
@@ -537,9 +540,11 @@ struct SsThread {
     uint4* bsm;  // sm + p.sm_beta_off
     uint4* bws;  // wsl + p.ws_beta_off
     uint4* a6;   // alpha[6]: always in shared memory, touched by every 64-LLR node
-    SS_DEV void bind(uint4* sm_, uint4* wsl_) {
+    uint4* wsh;  // the warp's block of the hot-level array + lane
+    SS_DEV void bind(uint4* sm_, uint4* wsl_, uint4* wsh_) {
         sm = sm_;
         wsl = wsl_;
+        wsh = wsh_;
         a6 = sm_ + p.aoff[6];
         bsm = sm_ + p.sm_beta_off;
         bws = wsl_ + p.ws_beta_off;
@@ -1071,7 +1076,7 @@ __global__ void __launch_bounds__(SCPD_SS_THREADS, 1) sc_decode_ss_kernel(const 
     }
     t.prof_on = PROF && p.prof != nullptr && warp == 0;
     const unsigned long long slot_id = (unsigned long long)blockIdx.x * nwarps + warp;
-    t.bind(sm_warp, p.ws + slot_id * p.ws_stride + lane);
+    t.bind(sm_warp, p.ws + slot_id * p.ws_stride + lane, p.hot + slot_id * p.hot_stride + lane);
     for (unsigned long long task = slot_id; task < p.ntasks; task += (unsigned long long)gridDim.x * nwarps) {
         t.pl = p.planes + task * p.planes_stride + lane;
         t.run();

@@ -160,6 +160,9 @@ struct scpd_decoder {
     size_t bs_planes_bytes = 0;
     // slot-sliced kernel plan (decode_ss.cuh): lane = frame; ss_ok == false: not available for this configuration
     int ber_batch_mb = 2048;  // LLR staging per batch of the Monte-Carlo loop
+    bool ss_l2persist = false;  // L2 persisting window over the hot-level array
+    uint4* d_ss_hot = nullptr;
+    size_t ss_hot_bytes = 0;
     int ss_pre = 0;  // leading f levels computed by the plane conversion
     bool ss_xf = false;  // the schedule holds fused SS_XF_* ops (kernel instantiation with XF)
     bool ss_ok = false;
@@ -342,9 +345,26 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
     const size_t per_warp = std::min<size_t>(total / d->ss_warps, (size_t)env_int("SCPD_SS_SMEM_KB", 1024) * 1024);
     // one alpha level in tensor memory: 512 columns shared by the warps that sit on the same 32 TMEM lanes
     const uint32_t tm_cols = 512u / (uint32_t)((d->ss_warps + 3) / 4);
+    // the smallest workspace level in its own dense array under an L2 persisting window (decode_ss): its lines are
+    // rewritten 2^(log2n - level) times per task and otherwise keep falling out of L2 into DRAM (47 % of the walk's DRAM
+    // writes at c2).  Measured: c2 443 -> 448, c3 336 -> 339, c1 382 -> 363 (not bound by DRAM): on from N = 4096.  The
+    // device's default set-aside (24.9 MB on B200) holds the array (19.4 MB for 2368 resident warps); a larger one costs the
+    // rest of the traffic dearly (40 MB: 404, 80 MB: 243 Gb/s at c2), so it is only raised when it is smaller than the array.
+    d->ss_l2persist = env_int("SCPD_SS_L2PERSIST", d->log2n >= 12 ? 1 : 0) != 0;
     if (!ss_make_plan(d->log2n, per_warp - 16, &d->ss_plan, env_int("SCPD_SS_LSA", -1), env_int("SCPD_SS_LWIN", -1), tm_cols,
-                      env_int("SCPD_SS_LTM", -1)))
+                      env_int("SCPD_SS_LTM", -1), d->ss_l2persist))
         return SCPD_OK;
+    if (d->ss_l2persist && d->ss_plan.lhot) {
+        int max_persist = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, d->device));
+        const size_t want = (size_t)d->num_sms * d->ss_warps * d->ss_plan.hot_stride * 16;
+        size_t cur = 0;
+        CUDA_TRY(cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize));
+        const size_t aside = std::min<size_t>((size_t)max_persist, std::max<size_t>(want, (size_t)env_int("SCPD_SS_L2PERSIST_MB", 0) << 20));
+        if (env_int("SCPD_VERBOSE", 0)) fprintf(stderr, "[scpd] L2 persisting: max %d B, hot array %zu B, set-aside %zu B (was %zu)\n", max_persist, want, aside, cur);
+        if (cur < aside && (size_t)max_persist >= want) CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside));
+        if ((size_t)max_persist < want) d->ss_l2persist = false;  // the array still exists, without the window
+    }
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * d->ss_warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // the leading f ops of the walk depend on the channel alone: the plane conversion computes them (decode_ss.cuh).
@@ -726,6 +746,7 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
     cudaFree(d->d_raw_ws);
     cudaFree(d->d_ss_sched);
     cudaFree(d->d_ss_ws);
+    cudaFree(d->d_ss_hot);
     cudaFree(d->d_ss_planes);
     cudaFree(d->d_ss_prof);
     for (int b = 0; b < 2; b++) {
@@ -874,6 +895,9 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     const unsigned long long grid = std::min<unsigned long long>((unsigned long long)d->num_sms, (ntasks + warps - 1) / warps);
     int rc = grow((void**)&d->d_ss_ws, &d->ss_ws_bytes, (size_t)(grid * warps * d->ss_plan.ws_stride * 16ull) + 16, st);
     if (rc) return rc;
+    const size_t hot_bytes = (size_t)(grid * warps) * d->ss_plan.hot_stride * 16;
+    rc = grow((void**)&d->d_ss_hot, &d->ss_hot_bytes, hot_bytes + 16, st);
+    if (rc) return rc;
     SsPre pre;
     const size_t pl_stride = ss_planes_quads(d->log2n, d->ss_pre, pre.off);
     rc = grow((void**)&d->d_ss_planes, &d->ss_planes_bytes, (size_t)ntasks * pl_stride * 16, st);
@@ -921,6 +945,9 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     p.ws_stride = d->ss_plan.ws_stride;
     p.ws_beta_off = d->ss_plan.ws_beta_off;
     for (int l = 0; l < 24; l++) p.aoff[l] = d->ss_plan.aoff[l];
+    p.hot = d->d_ss_hot;
+    p.lhot = d->ss_plan.lhot;
+    p.hot_stride = d->ss_plan.hot_stride;
     p.lpre = (uint32_t)(d->log2n - d->ss_pre);
     for (int l = 0; l < 24; l++) p.poff[l] = 0u;
     for (int s = 1; s <= d->ss_pre; s++) p.poff[d->log2n - s] = pre.off[s];
@@ -928,7 +955,27 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
     const size_t smem = (size_t)d->ss_plan.sm_stride * 16 * warps + (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0) + 16;
     ss_kernel_t k = ss_kernel_ptr((int)d->cfg.llr_bits, d->log2par, (int)d->cfg.extended, d->d_ss_prof != nullptr, d->ss_xf);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k0, st));
-    k<<<dim3((unsigned)grid), dim3((unsigned)(warps * 32)), smem, st>>>(p);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)(warps * 32));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        int nattr = 0;
+        if (d->ss_l2persist && d->ss_plan.lhot && hot_bytes) {
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = d->d_ss_hot;
+            attr[0].val.accessPolicyWindow.num_bytes = hot_bytes;
+            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            nattr = 1;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = nattr;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p));
+    }
     snprintf(d->last_kernel, sizeof d->last_kernel, "sc_decode_ss_kernel (slot-sliced, lane per frame, %d warps/CTA)", warps);
     if (d->timing) CUDA_TRY(cudaEventRecord(d->ev_k1, st));
     d->launches++;

@@ -281,6 +281,9 @@ struct SsPlan {
     uint32_t sm_beta_off = 0, sm_stride = 0;  // per warp
     uint32_t ws_beta_off = 0;
     unsigned long long ws_stride = 0;  // per warp
+    // the smallest workspace level (rewritten 2^(log2n - lhot) times per task) may live in its own dense array, one block
+    // of hot_stride uint4 per warp, so that an L2 persisting window can cover exactly those lines; 0 = in the workspace
+    uint32_t lhot = 0, hot_stride = 0;
     uint32_t win_words = 0;
 };
 // uint4 per 32-frame task: the channel planes, then alpha[log2n - s] of the leftmost node for s = 1 .. pre (the leading
@@ -308,7 +311,7 @@ static inline int ss_prefuse_depth(const std::vector<uint32_t>& ops, int log2n, 
 // tm_cols_avail: tensor-memory columns a warp may use (512 / ceil(warps per CTA / 4)), 0 = do not use tensor memory;
 // want_ltm: -1 = the largest level above lsa that fits, 0 = none, else that level.
 static inline bool ss_make_plan(int log2n, size_t smem_per_warp, SsPlan* out, int force_lsa = -1, int force_lwin = -1,
-                                uint32_t tm_cols_avail = 0, int want_ltm = 0) {
+                                uint32_t tm_cols_avail = 0, int want_ltm = 0, bool hot = false) {
     SsPlan p;
     auto a_quads = [](int l) { return (size_t)64u << (l - 5); };
     auto win_quads = [&](int lwin) { return (size_t)32u * std::max<size_t>(1, (std::min<size_t>((size_t)1 << lwin, (size_t)1 << log2n) / 32 + 3) / 4); };
@@ -348,6 +351,12 @@ static inline bool ss_make_plan(int log2n, size_t smem_per_warp, SsPlan* out, in
     size_t woff = 0;
     for (int l = lsa + 1; l <= log2n - 1; l++) {
         if (l == ltm) continue;
+        if (hot && p.lhot == 0) {  // the first (smallest) workspace level
+            p.lhot = (uint32_t)l;
+            p.hot_stride = (uint32_t)a_quads(l);
+            p.aoff[l] = 0;
+            continue;
+        }
         p.aoff[l] = (uint32_t)woff;
         woff += a_quads(l);
     }

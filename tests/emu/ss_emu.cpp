@@ -37,13 +37,13 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
         stats[3] = st.n_sub32_mixed;
     }
     SsPlan plan;
-    if (!ss_make_plan(log2n, smem_per_warp, &plan, force_lsa, force_lwin, ltm ? 512u : 0u, ltm)) return 1;
+    if (!ss_make_plan(log2n, smem_per_warp, &plan, force_lsa, force_lwin, ltm ? 512u : 0u, ltm, (xf & 2) != 0)) return 1;
     if (ltm > 0 && plan.ltm != (uint32_t)ltm) return 3;
     const size_t ntasks = (nframes + 31) / 32;
     // the leading f ops are computed with the planes (scpd_api.cu: plan_ss / decode_ss)
     const int pre = ss_prefuse_depth(sched, log2n, plan.lsa, max_pre);
     // xf: fused SS_XF_* ops wherever the three levels involved live in global memory (scpd_api.cu: large trees only)
-    sched = ss_build_schedule(log2n, pruning, flags, &st, fuse, xf ? (int)std::max(plan.lsa, plan.ltm) + 1 : 0, pre);
+    sched = ss_build_schedule(log2n, pruning, flags, &st, fuse, (xf & 1) ? (int)std::max(plan.lsa, plan.ltm) + 1 : 0, pre);
     if (stats) {
         stats[4] = (uint64_t)pre;
         stats[5] = st.n_xf;
@@ -105,11 +105,15 @@ static int run(int log2n, int pruning, const uint8_t* flags, const int8_t* llr, 
     std::vector<uint4> smem(plan.sm_stride, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     std::vector<uint4> ws(plan.ws_stride ? plan.ws_stride : 1, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     p.ws = ws.data();
+    std::vector<uint4> hotbuf(plan.hot_stride ? plan.hot_stride : 1, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    p.hot = hotbuf.data();
+    p.lhot = plan.lhot;
+    p.hot_stride = plan.hot_stride;
     std::vector<uint32_t> tmem((size_t)32 * 512, 0xDEADBEEFu);  // 512 columns per lane
     for (size_t task = 0; task < ntasks; task++) {
         for (int lane = 0; lane < 32; lane++) {
             SsThread<Q, LOG2PAR, EXT, false, true> t(p);
-            t.bind(smem.data() + lane, ws.data() + lane);
+            t.bind(smem.data() + lane, ws.data() + lane, hotbuf.data() + lane);
             t.sched = sched.data();
             t.tm = tmem.data() + (size_t)lane * 512;
             t.pl = planes.data() + task * pl_stride + lane;

@@ -691,9 +691,9 @@ def test_extract_info_and_roundtrip_full_size(scpd):
 
 
 def test_dispatch_by_batch_size(scpd):
-    """scpd_decode's kernel choice (profiles/tuning_r1.md): bit-sliced for large batches, the int16x2 kernel below the
-    crossover with lane groups that widen as the batch shrinks, a whole CTA per frame pair for the smallest batches of
-    large trees -- and the same bits whichever kernel runs."""
+    """scpd_decode's kernel choice (profiles/tuning_r1.md, tuning_r2.md): the slot-sliced kernel from 2.5 tasks of 32 frames
+    per SM, the int16x2 kernel below the crossover with lane groups that widen as the batch shrinks, a whole CTA per
+    frame pair for the smallest batches of large trees -- and the same bits whichever kernel runs."""
     import torch
     name, n, k, snr = CONFIG_SETS["c3"]
     flags = scpd.packed_flags(name, n)
@@ -701,12 +701,12 @@ def test_dispatch_by_batch_size(scpd):
     assert dec.last_kernel_name == ""
     llr = scpd.channel_generate(n, 16384, scpd.sigma(snr, k / n))
     seen = {}
-    for nfr in (16384, 12288, 6000, 4096, 1024, 64):
+    for nfr in (16384, 11000, 6000, 4096, 1024, 64):
         out = dec.decode(llr[:nfr])
         torch.cuda.synchronize()
         seen[nfr] = (dec.last_kernel_name, out[:8].cpu().numpy().view(np.uint32))
-    assert "bit-sliced" in seen[16384][0]
-    assert " 8 lanes" in seen[12288][0] and "16 lanes" in seen[6000][0] and "32 lanes" in seen[4096][0]
+    assert "slot-sliced" in seen[16384][0]
+    assert " 8 lanes" in seen[11000][0] and "16 lanes" in seen[6000][0] and "32 lanes" in seen[4096][0]
     assert "coop" in seen[1024][0] and "4 warps" in seen[1024][0] and "8 warps" in seen[64][0]
     want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr[:8].cpu().numpy(), threads=8)
     for nfr, (kname, got) in seen.items():

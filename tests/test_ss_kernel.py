@@ -128,5 +128,10 @@ def test_ss_fused_f_g_with_the_childs_opening_f(lsa, ltm, pre):
         got, st = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=64 * 1024, lsa=lsa, lwin=8, ltm=ltm, pre=pre, xf=1)
         assert (got == want).all(), prune
         assert st[5] > 0
+        # xf = 3: fused ops and the smallest workspace level in its own array (the one an L2 persisting window covers)
+        got, _ = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=64 * 1024, lsa=lsa, lwin=8, ltm=ltm, pre=pre, xf=3)
+        assert (got == want).all(), (prune, "hot")
     got, st = ss_emu(flags, n, 16, 8, 1, 2, llr, smem=64 * 1024, lsa=lsa, lwin=8, ltm=ltm, pre=pre, xf=0)
+    assert (got == want).all() and st[5] == 0
+    got, st = ss_emu(flags, n, 16, 8, 1, 2, llr, smem=64 * 1024, lsa=lsa, lwin=8, ltm=ltm, pre=pre, xf=2)
     assert (got == want).all() and st[5] == 0
