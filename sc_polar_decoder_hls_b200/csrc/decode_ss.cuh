@@ -154,14 +154,19 @@ SS_DEV H2 h2_from_sm(uint32_t wa, uint32_t wb, int c) {  // c folds to an immedi
 }
 // sign bits of 16 registers of +-1.0 pairs -> one word, bit 2j = low half of B[j]
 SS_DEV uint32_t h2_pack16(const H2 (&B)[16]) {
-    uint32_t acc = 0u;
+    // One IDP.4A per register: the bytes of +-1.0 pairs are (0, 0x3C | s_lo << 7, 0, 0x3C | s_hi << 7), so with the byte
+    // weights (0, 4^r, 0, 2 4^r) four registers add up to 0x3C * 3 * 85 + 128 * (their eight sign bits in order); the
+    // constant is folded into the start value.
+    uint32_t v[4];
 #pragma unroll
-    for (int j = 15; j >= 0; j--) {
-        // (B - 0x3C003C00) has the two sign bits at 15 and 31; times (1 + 2^15) brings them to 30 and 31
-        const uint32_t y = B[j].u * 0x8001u - 0x3C003C00u * 0x8001u;
-        acc = __funnelshift_l(y, acc, 2);
+    for (int g = 0; g < 4; g++) {
+        uint32_t acc = 0u - 0x3Cu * 3u * 85u;
+#pragma unroll
+        for (int r = 0; r < 4; r++) acc = __dp4a(B[4 * g + r].u, (uint32_t)((1u << (2 * r + 8)) | (2u << (2 * r + 24))), acc);
+        v[g] = acc;  // 128 * (8 sign bits)
     }
-    return acc;
+    const uint32_t lo = v[0] + (v[1] << 8), hi = v[2] + (v[3] << 8);  // 128 * (16 sign bits)
+    return (lo >> 7) | (hi << 9);
 }
 #else
 struct H2 {
