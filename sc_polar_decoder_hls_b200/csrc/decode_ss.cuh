@@ -414,21 +414,10 @@ SS_SIDE_PRAGMA
             B[i + 4] = Bc[i];
         }
     }
-    static SS_NOINLINE R8 walk16_fn(H2 a0, H2 a1, H2 a2, H2 a3, H2 a4, H2 a5, H2 a6, H2 a7, uint32_t ids, uint32_t fl,
-                                    uint32_t prune) {
-        const H2 A[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
-        R8 r;
-        walk16_body(A, ids, fl, prune, r.v);
-        return r;
-    }
+    // inlined into its two call sites in walk32: the routine itself is ~50 instructions, the call cost 19 register moves
+    // (c1 385 -> 393 Gb/s, 112 -> 104 registers); the 8-LLR routines behind dispatch8 stay out of line
     static SS_DEV void walk16(const H2 (&A)[8], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[8]) {
-#if SS_SIDE_UNROLL == 3
-        const R8 r = walk16_fn(A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], ids, fl, prune);
-#pragma unroll
-        for (int i = 0; i < 8; i++) B[i] = r.v[i];
-#else
         walk16_body(A, ids, fl, prune, B);
-#endif
     }
     // 32 LLRs (scale 1); ids: four pattern ids, fl: the 32 information flags
     static SS_DEV void walk32(const H2 (&A)[16], uint32_t ids, uint32_t fl, uint32_t prune, H2 (&B)[16]) {
