@@ -608,6 +608,35 @@ struct SsThread {
         const uint32_t half = 1u << (l - 6);
         const uint32_t* ub = (G && !zero) ? bword(l - 1, wd) : nullptr;  // words wd .. wd + half - 1 lie in one storage
         V a0, b0, a1, b1, r;
+        if constexpr (!SRC_TM && !DST_TM) {
+            // source and destination in global / shared memory (the levels that stream through DRAM at c2 and above): four
+            // chunk pairs per trip, three of them in flight while one is computed (half >= 4: f / g of a 128-LLR node is
+            // always the fused SS_XS, never this op).  c2 456 -> 471 Gb/s at 128 registers.  The same depth in the
+            // tensor-memory variants costs more in code than it hides in latency (c1 396 -> 388, c2 471 -> 447), and so
+            // does a second, shallower loop inlined beside this one (c1 379, c2 438).
+            V a2, b2, a3, b3;
+            load_pair<false>(src, 0, half, a0, b0);
+            load_pair<false>(src, 1, half, a1, b1);
+            load_pair<false>(src, 2, half, a2, b2);
+            for (uint32_t c = 0; c < half; c += 4) {
+                load_pair<false>(src, c + 3u, half, a3, b3);
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                if (G && !zero) u = *reinterpret_cast<const uint4*>(ub + (c >> 2) * 128u);
+                const bool more = c + 4u < half;
+                if constexpr (G) bs::g_sat_ca2<P>(a0, b0, u.x, r); else bs::f_op<P>(a0, b0, r);
+                store(dst + c * 64u, r);
+                if (more) load_pair<false>(src, c + 4u, half, a0, b0);
+                if constexpr (G) bs::g_sat_ca2<P>(a1, b1, u.y, r); else bs::f_op<P>(a1, b1, r);
+                store(dst + (c + 1u) * 64u, r);
+                if (more) load_pair<false>(src, c + 5u, half, a1, b1);
+                if constexpr (G) bs::g_sat_ca2<P>(a2, b2, u.z, r); else bs::f_op<P>(a2, b2, r);
+                store(dst + (c + 2u) * 64u, r);
+                if (more) load_pair<false>(src, c + 6u, half, a2, b2);
+                if constexpr (G) bs::g_sat_ca2<P>(a3, b3, u.w, r); else bs::f_op<P>(a3, b3, r);
+                store(dst + (c + 3u) * 64u, r);
+            }
+            return;
+        }
         load_pair<SRC_TM>(src, 0, half, a0, b0);
         for (uint32_t c = 0; c < half; c += 2) {
             load_pair<SRC_TM>(src, c + 1u, half, a1, b1);

@@ -338,7 +338,7 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
     if (d->cfg.extended && (((1u << (q - 1)) - 1u) << d->log2par) > 2047u) return SCPD_OK;
     ss_kernel_t k = ss_kernel_ptr(q, d->log2par, (int)d->cfg.extended);
     if (!k) return SCPD_OK;
-    d->ss_sched_host = ss_build_schedule(d->log2n, (int)d->cfg.pruning, flags, &d->ss_stats, env_int("SCPD_SS_FUSE", 1));
+    d->ss_sched_host = ss_build_schedule(d->log2n, (int)d->cfg.pruning, flags, &d->ss_stats, 1);
     d->ss_warps = std::max(1, std::min(SCPD_SS_THREADS / 32, env_int("SCPD_SS_WARPS", SCPD_SS_THREADS / 32)));
     d->ss_sched_smem = d->ss_sched_host.size() <= (size_t)env_int("SCPD_SS_SCHED_SMEM_WORDS", 2048);
     const size_t total = (size_t)227 * 1024 - (d->ss_sched_smem ? d->ss_sched_host.size() * 4 : 0);
@@ -376,7 +376,7 @@ static int plan_ss(scpd_decoder* d, const uint8_t* flags) {
     // that opens the child, so that level is not read back (SS_XF_*, a separate instantiation of the kernel)
     d->ss_xf = d->log2n >= env_int("SCPD_SS_XF_MIN_LOG2N", 15) && ss_kernel_ptr(q, d->log2par, (int)d->cfg.extended, false, true);
     const int xf_min = d->ss_xf ? (int)std::max(d->ss_plan.lsa, d->ss_plan.ltm) + 1 : 0;
-    d->ss_sched_host = ss_build_schedule(d->log2n, (int)d->cfg.pruning, flags, &d->ss_stats, env_int("SCPD_SS_FUSE", 1), xf_min,
+    d->ss_sched_host = ss_build_schedule(d->log2n, (int)d->cfg.pruning, flags, &d->ss_stats, 1, xf_min,
                                          d->ss_pre);
     if (d->ss_xf)
         CUDA_TRY(cudaFuncSetAttribute((const void*)ss_kernel_ptr(q, d->log2par, (int)d->cfg.extended, false, true),

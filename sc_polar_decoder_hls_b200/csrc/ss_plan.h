@@ -68,7 +68,7 @@ struct SsStats {
 
 struct SsBuilder {
     int log2n = 0, pruning = 0;
-    int fuse = 1;  // 1: emit SS_XS for the level-7 op in front of a 64-LLR node
+    int fuse = 1;  // (kept for the callers' signature: the level-7 op is always SS_XS)
     int xf_min = 0;  // > 0: fuse an f / g op at level l with the f that opens its child when l - 2 >= xf_min
     int lead_skip = 0;  // the f ops of the leftmost nodes of the top lead_skip levels are computed by ss_planes_kernel
     const uint8_t* flags = nullptr;
@@ -140,7 +140,7 @@ struct SsBuilder {
     void emit_x(uint32_t kind, int l, uint32_t o, uint32_t oc) {
         const uint32_t h = 1u << (l - 1);
         if (kind == SS_F) st.n_f += h; else st.n_g += h;
-        if (l == 7 && fuse >= 1 && !(pruning >= 1 && count(oc, 64) == 0)) {
+        if (l == 7) {  // always fused: the plain f / g op pipelines four chunk pairs and does not exist at level 7
             // fused with the 64-LLR child (which is never all-frozen here: the caller prunes those)
             ops.push_back(ss_op_make(SS_XS, 7, oc));
             push_sub_words(oc, kind);

@@ -65,7 +65,7 @@ def _check(scpd, name, n, k, par, q, ext, prune, llr, via="device", fmt=0):
 
 
 @pytest.fixture(params=["auto", "generic", "raw", "fast2", "fast8", "fast16", "fast32", "coop4", "coop8", "bs8", "bs16", "bs32", "bs32ws",
-                        "ss", "ss12", "ss_notm", "ss_tm8", "ss_nofuse", "ss_xf", "ss_pre0", "ss_pre3"])
+                        "ss", "ss12", "ss_notm", "ss_tm8", "ss_xf", "ss_pre0", "ss_pre3"])
 def kernel_mode(request, monkeypatch):
     """Selects the decode kernel through the library's environment switches (read in scpd_create):
     the bit-sliced kernel with 8 / 16 / 32 lanes per frame group (bs32ws: partial sums pushed out to the
@@ -73,12 +73,12 @@ def kernel_mode(request, monkeypatch):
     generic kernel, the raw-pattern kernel, and the library's own choice."""
     mode = request.param
     for v in ("SCPD_KERNEL", "SCPD_GROUP", "SCPD_COOP", "SCPD_BS_GROUP", "SCPD_BS_LSB", "SCPD_BS_WARPS", "SCPD_SS_WARPS",
-              "SCPD_SS_LTM", "SCPD_SS_LSA", "SCPD_SS_LWIN", "SCPD_SS_FUSE", "SCPD_SS_XF_MIN_LOG2N", "SCPD_SS_PRE"):
+              "SCPD_SS_LTM", "SCPD_SS_LSA", "SCPD_SS_LWIN", "SCPD_SS_XF_MIN_LOG2N", "SCPD_SS_PRE"):
         monkeypatch.delenv(v, raising=False)
     if mode.startswith("ss"):
         # the slot-sliced kernel (a lane per frame): default plan (16 warps per CTA, one LLR level in tensor memory),
         # 12 warps (other tensor-memory column split), no tensor memory, level 8 in tensor memory with a small
-        # partial-sum window, no fused level-7 op
+        # partial-sum window
         monkeypatch.setenv("SCPD_KERNEL", "ss")
         if mode == "ss12":
             monkeypatch.setenv("SCPD_SS_WARPS", "12")
@@ -87,8 +87,6 @@ def kernel_mode(request, monkeypatch):
         elif mode == "ss_tm8":
             monkeypatch.setenv("SCPD_SS_LTM", "8")
             monkeypatch.setenv("SCPD_SS_LWIN", "8")
-        elif mode == "ss_nofuse":
-            monkeypatch.setenv("SCPD_SS_FUSE", "0")
         elif mode == "ss_xf":      # f / g fused with the child's opening f wherever three levels stream through global memory
             monkeypatch.setenv("SCPD_SS_XF_MIN_LOG2N", "10")
         elif mode == "ss_pre0":    # every f level computed by the walk

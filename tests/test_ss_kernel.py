@@ -60,9 +60,9 @@ def test_ss_kernel_storage_plans(lsa, lwin, ltm):
     flags = scpd.packed_flags(name, n)
     llr = _llrs(np.random.default_rng(abs(lsa) * 10 + ltm), n, k, 8, nfr=10)
     want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr)
-    for prune, fuse in ((0, 1), (2, 1), (2, 0)):   # fuse 0: no fused level-7 op in front of the 64-LLR nodes
-        got, _ = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=64 * 1024, lsa=lsa, lwin=lwin, ltm=ltm, fuse=fuse)
-        assert (got == want).all(), (prune, fuse)
+    for prune in (0, 1, 2):
+        got, _ = ss_emu(flags, n, 16, 8, 1, prune, llr, smem=64 * 1024, lsa=lsa, lwin=lwin, ltm=ltm)
+        assert (got == want).all(), prune
 
 
 def test_ss_kernel_arbitrary_flag_tables():
