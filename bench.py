@@ -22,6 +22,7 @@ the full un-pruned tree (the reference FSM at PRUNING_LEVEL 0); the results are 
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -35,13 +36,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-# BASELINE.json configs: table, N, K, Eb/N0, frames per step of the device-resident measurement
+# BASELINE.json configs: table, N, K, Eb/N0, frames per step of the device-resident measurement.  The large
+# trees are measured on whole rounds of the resident warps (148 SMs x 16 warps x 32 frames = 75 776 frames a round:
+# c3 two rounds, c4 one, c5 2^16 frames = 2048 of the 2368 warps; `profiles/tuning_r2.md` "Batches in whole rounds").
 CONFIGS = {
     "c1": dict(name="FB_N1024_K512", n=1024, k=512, ebn0=2.5, frames=1 << 20, check=256),
     "c2": dict(name="frozen_n_4096_k_3072", n=4096, k=3072, ebn0=3.5, frames=1 << 20, check=256),
-    "c3": dict(name="frozen_n_32768_k_29492_snr_4_5", n=32768, k=29492, ebn0=4.5, frames=1 << 17, check=64),
-    "c4": dict(name="frozen_n_131072_k_117964", n=131072, k=117964, ebn0=4.5, frames=1 << 16, check=16),
-    "c5": dict(name="frozen_n_524288_k_262144", n=524288, k=262144, ebn0=2.0, frames=1 << 15, check=4),
+    "c3": dict(name="frozen_n_32768_k_29492_snr_4_5", n=32768, k=29492, ebn0=4.5, frames=151552, check=64),
+    "c4": dict(name="frozen_n_131072_k_117964", n=131072, k=117964, ebn0=4.5, frames=75776, check=16),
+    "c5": dict(name="frozen_n_524288_k_262144", n=524288, k=262144, ebn0=2.0, frames=1 << 16, check=4),
 }
 HEAD = "c2"
 CFG = dict(CONFIGS[HEAD], par=16, llr_bits=8)
@@ -229,38 +232,56 @@ def rooflines(n, frames, ms, peaks, sms, sm_mhz):
 
 
 def measure_config(scpd, torch, key, dev, local, steps, warmup, peaks, sms, sm_mhz):
-    """Device-resident throughput of one BASELINE config on this GPU, with its own parity spot check."""
+    """Device-resident throughput of one BASELINE config on this GPU, with its own parity spot check.  A batch that does
+    not fit the free device memory (c5: ~130 GB of LLRs, planes and workspace) is halved once and the line says so."""
+    err = None
+    try:
+        return _measure_config(scpd, torch, key, CONFIGS[key]["frames"], dev, local, steps, warmup, peaks, sms, sm_mhz)
+    except (scpd.ScpdError, torch.OutOfMemoryError) as e:
+        err = str(e)[:120]  # the traceback (and the tensors of the failed attempt it holds) goes with the except block
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    out = _measure_config(scpd, torch, key, CONFIGS[key]["frames"] // 2, dev, local, steps, warmup, peaks, sms, sm_mhz)
+    out["batch_halved_after"] = err
+    return out
+
+
+def _measure_config(scpd, torch, key, frames, dev, local, steps, warmup, peaks, sms, sm_mhz):
     import oracle_lib as ol
     c = CONFIGS[key]
-    n, k, frames = c["n"], c["k"], c["frames"]
+    n, k = c["n"], c["k"]
     flags = scpd.packed_flags(c["name"], n)
     dec = scpd.Decoder(n, k, flags, par=16, llr_bits=8, fmt=scpd.FMT_CA2, extended=1, pruning=scpd.PRUNE_R0_R1, device=local)
-    llr = scpd.channel_generate(n, frames, scpd.sigma(c["ebn0"], k / n), device=local)
-    xhat = torch.empty((frames, n // 32), dtype=torch.int32, device=dev)
-    dec.decode(llr, xhat)
-    torch.cuda.synchronize()
-    chk = c["check"]
-    idx = np.r_[0:chk, frames - chk:frames]
-    want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr[idx].cpu().numpy(), threads=16)
-    ok = bool((xhat[idx].cpu().numpy().view(np.uint32) == want).all())
-    assert ok, f"{key}: CUDA decode differs from the oracle"
-    for _ in range(warmup):
+    llr = xhat = None
+    try:
+        llr = scpd.channel_generate(n, frames, scpd.sigma(c["ebn0"], k / n), device=local)
+        xhat = torch.empty((frames, n // 32), dtype=torch.int32, device=dev)
         dec.decode(llr, xhat)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        dec.decode(llr, xhat)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    out = {"name": key, "n": n, "k": k, "ebn0_db": c["ebn0"], "batch": frames, "value": frames * k / (ms * 1e-3) / 1e9,
-           "unit": UNIT, "ms": ms, "kernel": dec.last_kernel_name, "parity_frames_checked": int(len(idx)),
-           "roofline": rooflines(n, frames, ms, peaks, sms, sm_mhz)}
-    dec.close()
-    del llr, xhat
-    torch.cuda.empty_cache()
-    return out
+        torch.cuda.synchronize()
+        chk = c["check"]
+        idx = np.r_[0:chk, frames - chk:frames]
+        want = ol.decode_packed(n, 16, 8, 0, 1, flags, llr[idx].cpu().numpy(), threads=16)
+        ok = bool((xhat[idx].cpu().numpy().view(np.uint32) == want).all())
+        assert ok, f"{key}: CUDA decode differs from the oracle"
+        for _ in range(warmup):
+            dec.decode(llr, xhat)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            dec.decode(llr, xhat)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"name": key, "n": n, "k": k, "ebn0_db": c["ebn0"], "batch": frames, "value": frames * k / (ms * 1e-3) / 1e9,
+               "unit": UNIT, "ms": ms, "kernel": dec.last_kernel_name, "parity_frames_checked": int(len(idx)),
+               "roofline": rooflines(n, frames, ms, peaks, sms, sm_mhz)}
+        return out
+    finally:
+        dec.close()
+        del llr, xhat
+        torch.cuda.empty_cache()
 
 
 def measure_pipeline(scpd, key, local, nframes):

@@ -1208,16 +1208,45 @@ extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
 
 extern "C" const char* scpd_last_kernel_name(const scpd_decoder* d) { return d ? d->last_kernel : ""; }
 
+// u = x F^(x)n of whole frames: in registers (one pass over memory) for 32 <= n <= 32768, through the output buffer above
+static cudaError_t launch_polar_transform(uint32_t wpf, uint32_t n, size_t nframes, const uint32_t* src, uint32_t* dst,
+                                          int num_sms, cudaStream_t st) {
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((nframes + 7) / 8, (unsigned long long)num_sms * 8);
+#define TR(W) polar_transform_reg_kernel<W><<<blocks, 256, 0, st>>>(wpf, nframes, src, dst)
+    if (n < 32 || wpf > 1024) polar_transform_kernel<<<(unsigned)((nframes + 3) / 4), 128, 0, st>>>(wpf, n, nframes, src, dst);
+    else if (wpf <= 32) TR(1);
+    else if (wpf <= 64) TR(2);
+    else if (wpf <= 128) TR(4);
+    else if (wpf <= 256) TR(8);
+    else if (wpf <= 512) TR(16);
+    else TR(32);
+#undef TR
+    return cudaGetLastError();
+}
+// all ten counters of the Monte-Carlo loop from one pass over x^ (32 <= n <= 32768); false = not available for this n
+static bool launch_count_all(uint32_t wpf, uint32_t n, uint32_t k, size_t nframes, const uint32_t* xhat, const uint32_t* ref,
+                             int per_frame, const uint32_t* mask, unsigned long long* cnt, int num_sms, cudaStream_t st) {
+    if (n < 32 || wpf > 1024) return false;
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((nframes + 7) / 8, (unsigned long long)num_sms * 8);
+#define CA(W) count_all_kernel<W><<<blocks, 256, 0, st>>>(wpf, n, k, nframes, xhat, ref, per_frame, mask, cnt)
+    if (wpf <= 32) CA(1);
+    else if (wpf <= 64) CA(2);
+    else if (wpf <= 128) CA(4);
+    else if (wpf <= 256) CA(8);
+    else if (wpf <= 512) CA(16);
+    else CA(32);
+#undef CA
+    return true;
+}
+
 extern "C" int scpd_extract_info(scpd_decoder* d, const uint32_t* d_xhat, size_t nframes, uint32_t* d_uhat,
                                  void* stream) {
     if (!d) return set_error(SCPD_E_ARG, "scpd_extract_info: null decoder");
     if (nframes == 0) return SCPD_OK;
     if (!d_xhat || !d_uhat) return set_error(SCPD_E_ARG, "scpd_extract_info: null buffer");
     CUDA_TRY(cudaSetDevice(d->device));
-    const unsigned grid = (unsigned)((nframes + 3) / 4);
-    polar_transform_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d->wpf, d->cfg.n, nframes, d_xhat, d_uhat);
+    CUDA_TRY(launch_polar_transform(d->wpf, d->cfg.n, nframes, d_xhat, d_uhat, d->num_sms, (cudaStream_t)stream));
     d->launches++;
-    CUDA_TRY(cudaGetLastError());
     return SCPD_OK;
 }
 
@@ -1439,8 +1468,10 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
             CUDA_TRY(keep((void**)&d->d_ber_ref[b], &d->ber_ref_bytes[b], batch * (size_t)wpf * 4));
             tmp.ref[b] = d->d_ber_ref[b];
         }
-    CUDA_TRY(keep((void**)&d->d_ber_diff, &d->ber_diff_bytes, batch * (size_t)wpf * 4));
-    tmp.diff = d->d_ber_diff;
+    if (n < 32 || wpf > 1024) {  // x^ ^ x of a batch, for the counters that cannot hold a frame in registers
+        CUDA_TRY(keep((void**)&d->d_ber_diff, &d->ber_diff_bytes, batch * (size_t)wpf * 4));
+        tmp.diff = d->d_ber_diff;
+    }
     cudaStream_t sg = d->st_in, sd = d->st_comp;  // generator stream, decode + count stream
     CUDA_TRY(cudaMemsetAsync(tmp.cnt, 0, 10 * sizeof(unsigned long long), sd));
     const float sigma = scpd_sigma(ebn0_db, rate);
@@ -1455,7 +1486,7 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
         if (per_frame_ref) {
             if (src_mode == SCPD_SRC_RANDOM) {
                 payload_kernel<<<gblocks, 256, 0, sg>>>(wpf, first_frame + done, nb, payload_seed, tmp.mask, tmp.ref[b]);
-                polar_transform_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, sg>>>(wpf, n, nb, tmp.ref[b], tmp.ref[b]);
+                CUDA_TRY(launch_polar_transform(wpf, n, nb, tmp.ref[b], tmp.ref[b], d->num_sms, sg));
             } else {
                 ref_cycle_kernel<<<gblocks, 256, 0, sg>>>(wpf, first_frame + done, nb, tmp.cws, ncw, tmp.ref[b]);
             }
@@ -1471,6 +1502,12 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
         rc = scpd_decode(d, d->d_llr2[b], nb, d->d_xhat2[b], sd);
         if (rc) break;
         const uint32_t* ref = per_frame_ref ? tmp.ref[b] : tmp.cws;  // nullptr = all-zero
+        if (launch_count_all(wpf, n, d->cfg.k, nb, d->d_xhat2[b], ref, per_frame_ref ? 1 : 0, tmp.mask, tmp.cnt, d->num_sms, sd)) {
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(d->ev_out[b], sd));
+            d->launches += 2;  // channel, counters
+            continue;
+        }
         rc = scpd_count_errors(n, nb, d->d_xhat2[b], ref, per_frame_ref ? 1 : 0, (uint64_t*)tmp.cnt, sd);
         if (rc) break;
         // information bits: (x^ ^ x) F^(x)n on the information positions

@@ -634,6 +634,45 @@ def test_run_ber_ex_codeword_cycle_and_random_payload(scpd):
     dec.close()
 
 
+@pytest.mark.parametrize("n", [8, 32, 256, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+def test_run_ber_counters_and_transform_every_frame_size(scpd, n):
+    """The ten counters of scpd_run_ber_ex and scpd_extract_info for every instantiation of the register-resident
+    kernels (count_all_kernel / polar_transform_reg_kernel: 1 ... 32 words per lane, fewer than 32 words per frame) and
+    for the sizes on either side that keep the multi-pass kernels (n < 32, n > 32768).  The decode is not what is
+    tested here (the product's own output is the input of the host counts): all-zero codeword, one stored codeword,
+    random payloads, on a table that is not polar-structured, at a noise level that leaves errors in most frames."""
+    import torch
+    rng = np.random.default_rng(n)
+    flags = (rng.random(n) < 0.5).astype(np.uint8)
+    flags[-1] = 1
+    k = int(flags.sum())
+    nfr, first, snr = (300 if n <= 4096 else 96), 1234567, 1.0
+    dec = scpd.Decoder(n, k, flags, par=min(16, n // 2))
+
+    def host_counts(x):  # x: None, [n] or [nfr, n]
+        llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n), first_frame=first, codeword=x).cpu().numpy()
+        xhat = ol.unpack_bits(dec.decode_host(llr), n)
+        sent = np.zeros((nfr, n), np.uint8) if x is None else np.broadcast_to(x, (nfr, n))
+        want = ol.count_errors(n, xhat, sent)
+        e = ol.polar_transform(xhat ^ sent)[:, flags == 1].sum(axis=1)
+        return want + [int(e.sum()), int((e != 0).sum()), nfr * k, nfr]
+
+    assert dec.run_ber_ex(snr, k / n, nfr, first_frame=first) == host_counts(None)
+    cw = ol.polar_transform((rng.integers(0, 2, n).astype(np.uint8) & flags)[None, :])[0]
+    got = dec.run_ber_ex(snr, k / n, nfr, first_frame=first, codewords=cw)
+    assert got == host_counts(cw)
+    assert got[1] > 0 and got[7] > 0
+    x = ol.polar_transform(ol.unpack_bits(scpd.payload_words(9, first, nfr, flags), n))
+    assert dec.run_ber_ex(snr, k / n, nfr, first_frame=first, random_payload=True, payload_seed=9) == host_counts(x)
+    # the transform on its own
+    w = rng.integers(0, 1 << 32, size=(nfr, max(1, n // 32)), dtype=np.uint64).astype(np.uint32)
+    if n < 32:
+        w &= np.uint32((1 << n) - 1)
+    got_u = dec.extract_info(torch.from_numpy(w.view(np.int32)).cuda()).cpu().numpy().view(np.uint32)
+    assert (got_u == ol.pack_bits(ol.polar_transform(ol.unpack_bits(w, n)))).all()
+    dec.close()
+
+
 def test_stage_time_matrix(scpd):
     """scpd_stage_time: measured cycles per function x level.  Visits must equal the schedule's op counts
     times the number of profiled warps; cycles must be positive exactly where there are visits; the 64-LLR nodes (row R)
