@@ -200,6 +200,9 @@ struct scpd_decoder {
     int8_t* d_llr2[2] = {nullptr, nullptr};
     uint32_t* d_xhat2[2] = {nullptr, nullptr};
     size_t pipe_frames = 0;
+    int pipe_llr_bufs = 0;                 // LLR staging buffers behind d_llr2 (2, or 1 for the large trees of the Monte-Carlo loop)
+    cudaEvent_t ev_llr_free = nullptr;     // recorded by decode_ss once the plane conversion has consumed the LLRs
+    bool llr_free_recorded = false;
     // staging for scpd_decode_host / scpd_run_ber
     int8_t* d_llr = nullptr;
     uint32_t* d_xhat = nullptr;
@@ -756,6 +759,7 @@ extern "C" void scpd_destroy(scpd_decoder* d) {
         if (d->ev_dec[b]) cudaEventDestroy(d->ev_dec[b]);
         if (d->ev_out[b]) cudaEventDestroy(d->ev_out[b]);
     }
+    if (d->ev_llr_free) cudaEventDestroy(d->ev_llr_free);
     if (d->ev_k0) cudaEventDestroy(d->ev_k0);
     if (d->ev_k1) cudaEventDestroy(d->ev_k1);
     if (d->st_in) cudaStreamDestroy(d->st_in);
@@ -922,6 +926,10 @@ static int decode_ss(scpd_decoder* d, const int8_t* d_llr, size_t nframes, uint3
 #undef SS_PLANES
         d->launches++;
         CUDA_TRY(cudaGetLastError());
+        if (d->ev_llr_free) {  // the walk reads planes only: the caller's LLR buffer is free from here (scpd_run_ber_ex)
+            CUDA_TRY(cudaEventRecord(d->ev_llr_free, st));
+            d->llr_free_recorded = true;
+        }
     }
     SsParams p;
     p.sched = d->d_ss_sched;
@@ -1101,7 +1109,7 @@ static int ensure_stage(scpd_decoder* d, size_t nframes) {
     return SCPD_OK;
 }
 
-static int ensure_pipeline(scpd_decoder* d, size_t chunk) {
+static int ensure_pipeline(scpd_decoder* d, size_t chunk, int llr_bufs = 2) {
     if (!d->st_in) {
         CUDA_TRY(cudaStreamCreateWithFlags(&d->st_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&d->st_comp, cudaStreamNonBlocking));
@@ -1111,8 +1119,10 @@ static int ensure_pipeline(scpd_decoder* d, size_t chunk) {
             CUDA_TRY(cudaEventCreateWithFlags(&d->ev_dec[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&d->ev_out[b], cudaEventDisableTiming));
         }
+        CUDA_TRY(cudaEventCreateWithFlags(&d->ev_llr_free, cudaEventDisableTiming));
     }
-    if (chunk <= d->pipe_frames) return SCPD_OK;
+    if (chunk <= d->pipe_frames && llr_bufs <= d->pipe_llr_bufs) return SCPD_OK;
+    chunk = std::max(chunk, d->pipe_frames);
     for (int b = 0; b < 2; b++) {
         cudaFree(d->d_llr2[b]);
         cudaFree(d->d_xhat2[b]);
@@ -1120,11 +1130,13 @@ static int ensure_pipeline(scpd_decoder* d, size_t chunk) {
         d->d_xhat2[b] = nullptr;
     }
     d->pipe_frames = 0;
+    d->pipe_llr_bufs = 0;
     for (int b = 0; b < 2; b++) {
-        CUDA_TRY(cudaMalloc(&d->d_llr2[b], chunk * (size_t)d->cfg.n));
+        if (b < llr_bufs) CUDA_TRY(cudaMalloc(&d->d_llr2[b], chunk * (size_t)d->cfg.n));
         CUDA_TRY(cudaMalloc(&d->d_xhat2[b], chunk * (size_t)d->wpf * 4));
     }
     d->pipe_frames = chunk;
+    d->pipe_llr_bufs = llr_bufs;
     return SCPD_OK;
 }
 
@@ -1208,12 +1220,28 @@ extern "C" const char* scpd_kernel_name(const scpd_decoder* d) {
 
 extern "C" const char* scpd_last_kernel_name(const scpd_decoder* d) { return d ? d->last_kernel : ""; }
 
-// u = x F^(x)n of whole frames: in registers (one pass over memory) for 32 <= n <= 32768, through the output buffer above
+// One CTA per frame with the frame in shared memory (N > 32768): grid and dynamic shared memory, 0 blocks = does not fit
+static unsigned smem_frame_grid(const void* kernel, uint32_t wpf, size_t nframes, int num_sms, size_t* smem) {
+    *smem = (size_t)wpf * 4;
+    if (*smem > 200u * 1024u) return 0;
+    if (*smem > 48u * 1024u && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    const unsigned long long per_sm = std::max<unsigned long long>(1, std::min<unsigned long long>(8, (220u * 1024u) / *smem));
+    return (unsigned)std::min<unsigned long long>(nframes, per_sm * (unsigned long long)num_sms);
+}
+// u = x F^(x)n of whole frames: in registers (one pass over memory) for 32 <= n <= 32768, in shared memory above that,
+// through the output buffer for n < 32 (and frames beyond the shared memory of an SM)
 static cudaError_t launch_polar_transform(uint32_t wpf, uint32_t n, size_t nframes, const uint32_t* src, uint32_t* dst,
                                           int num_sms, cudaStream_t st) {
     const unsigned blocks = (unsigned)std::min<unsigned long long>((nframes + 7) / 8, (unsigned long long)num_sms * 8);
+    size_t smem = 0;
+    unsigned grid = 0;
 #define TR(W) polar_transform_reg_kernel<W><<<blocks, 256, 0, st>>>(wpf, nframes, src, dst)
-    if (n < 32 || wpf > 1024) polar_transform_kernel<<<(unsigned)((nframes + 3) / 4), 128, 0, st>>>(wpf, n, nframes, src, dst);
+    if (n >= 32 && wpf > 1024 && (grid = smem_frame_grid((const void*)polar_transform_smem_kernel, wpf, nframes, num_sms, &smem)) != 0)
+        polar_transform_smem_kernel<<<grid, 256, smem, st>>>(wpf, nframes, src, dst);
+    else if (n < 32 || wpf > 1024) polar_transform_kernel<<<(unsigned)((nframes + 3) / 4), 128, 0, st>>>(wpf, n, nframes, src, dst);
     else if (wpf <= 32) TR(1);
     else if (wpf <= 64) TR(2);
     else if (wpf <= 128) TR(4);
@@ -1223,10 +1251,17 @@ static cudaError_t launch_polar_transform(uint32_t wpf, uint32_t n, size_t nfram
 #undef TR
     return cudaGetLastError();
 }
-// all ten counters of the Monte-Carlo loop from one pass over x^ (32 <= n <= 32768); false = not available for this n
+// all ten counters of the Monte-Carlo loop from one pass over x^ (n >= 32); false = not available for this n
 static bool launch_count_all(uint32_t wpf, uint32_t n, uint32_t k, size_t nframes, const uint32_t* xhat, const uint32_t* ref,
                              int per_frame, const uint32_t* mask, unsigned long long* cnt, int num_sms, cudaStream_t st) {
-    if (n < 32 || wpf > 1024) return false;
+    if (n < 32) return false;
+    if (wpf > 1024) {
+        size_t smem = 0;
+        const unsigned grid = smem_frame_grid((const void*)count_all_smem_kernel, wpf, nframes, num_sms, &smem);
+        if (!grid) return false;
+        count_all_smem_kernel<<<grid, 256, smem, st>>>(wpf, n, k, nframes, xhat, ref, per_frame, mask, cnt);
+        return true;
+    }
     const unsigned blocks = (unsigned)std::min<unsigned long long>((nframes + 7) / 8, (unsigned long long)num_sms * 8);
 #define CA(W) count_all_kernel<W><<<blocks, 256, 0, st>>>(wpf, n, k, nframes, xhat, ref, per_frame, mask, cnt)
     if (wpf <= 32) CA(1);
@@ -1417,10 +1452,35 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
         const size_t round = (size_t)d->num_sms * (size_t)d->ss_warps * 32;
         if (batch >= round) batch = batch / round * round;
     }
+    // Large trees: a batch of the size above leaves the slot-sliced kernel with half its warps (c5: 37 888 frames for the
+    // 75 776 the machine holds) and two 20 GB LLR buffers.  The walk reads planes only, so ONE LLR buffer does -- batch
+    // i + 1 is generated into it as soon as the plane conversion of batch i is through (ev_llr_free), overlapping the
+    // walk exactly as two buffers would -- and the batch grows towards a full round, as far as 85 % of the free memory
+    // carries LLRs, planes, workspace (about n bytes per resident frame) and output; the frames of the call are then
+    // split evenly over the batches.
+    int llr_bufs = 2;
+    if (d->ss_ok && d->log2n <= d->ss_max_log2n) {
+        const size_t round = (size_t)d->num_sms * (size_t)d->ss_warps * 32;
+        size_t free_b = 0, total_b = 0;
+        if (batch < round && nframes > batch && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            SsPre pre;
+            const size_t per_frame = (size_t)n + (ss_planes_quads(d->log2n, d->ss_pre, pre.off) * 16) / 32 + 3 * (size_t)wpf * 4;
+            free_b += d->pipe_frames * ((size_t)d->pipe_llr_bufs * n + 2 * (size_t)wpf * 4) + d->ss_planes_bytes + d->ss_ws_bytes;
+            const double budget = 0.85 * (double)free_b - 1.1 * (double)round * (double)n;
+            size_t fit = budget > 0 ? (size_t)(budget / (double)per_frame) : 0;
+            fit = std::min(fit, round) & ~(size_t)31;
+            if (fit > batch) {
+                const size_t nb = (size_t)((nframes + fit - 1) / fit);
+                batch = (size_t)(((nframes + nb - 1) / nb + 31) & ~(uint64_t)31);
+                llr_bufs = 1;
+            }
+        }
+    }
     if (batch > nframes) batch = (size_t)nframes;
     if (batch == 0) return SCPD_OK;
-    int rc = ensure_pipeline(d, batch);
+    int rc = ensure_pipeline(d, batch, llr_bufs);
     if (rc) return rc;
+    llr_bufs = d->pipe_llr_bufs;  // an earlier call may have left two
     const bool per_frame_ref = src_mode == SCPD_SRC_RANDOM || ncw > 1;
     struct Tmp {  // small per-call buffers, freed on every exit; the large scratch lives in the handle
         uint8_t* cw = nullptr;
@@ -1468,10 +1528,6 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
             CUDA_TRY(keep((void**)&d->d_ber_ref[b], &d->ber_ref_bytes[b], batch * (size_t)wpf * 4));
             tmp.ref[b] = d->d_ber_ref[b];
         }
-    if (n < 32 || wpf > 1024) {  // x^ ^ x of a batch, for the counters that cannot hold a frame in registers
-        CUDA_TRY(keep((void**)&d->d_ber_diff, &d->ber_diff_bytes, batch * (size_t)wpf * 4));
-        tmp.diff = d->d_ber_diff;
-    }
     cudaStream_t sg = d->st_in, sd = d->st_comp;  // generator stream, decode + count stream
     CUDA_TRY(cudaMemsetAsync(tmp.cnt, 0, 10 * sizeof(unsigned long long), sd));
     const float sigma = scpd_sigma(ebn0_db, rate);
@@ -1481,6 +1537,7 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
         const int b = (int)(i & 1);
         const size_t nb = (size_t)((nframes - done < batch) ? nframes - done : batch);
         if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(sg, d->ev_out[b], 0));  // batch i - 2 has been decoded and counted
+        int8_t* const llr_buf = d->d_llr2[llr_bufs == 2 ? b : 0];
         const uint8_t* cw_arg = tmp.cw;
         int cw_mode = 0;
         if (per_frame_ref) {
@@ -1495,18 +1552,28 @@ extern "C" int scpd_run_ber_ex(scpd_decoder* d, float ebn0_db, float rate, uint6
             cw_mode = 2;
             d->launches += src_mode == SCPD_SRC_RANDOM ? 2 : 1;
         }
-        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, cw_arg, cw_mode, d->d_llr2[b], sg);
+        rc = scpd_channel_generate(n, first_frame + done, nb, seed, sigma, cw_arg, cw_mode, llr_buf, sg);
         if (rc) break;
         CUDA_TRY(cudaEventRecord(d->ev_in[b], sg));
         CUDA_TRY(cudaStreamWaitEvent(sd, d->ev_in[b], 0));
-        rc = scpd_decode(d, d->d_llr2[b], nb, d->d_xhat2[b], sd);
+        d->llr_free_recorded = false;
+        rc = scpd_decode(d, llr_buf, nb, d->d_xhat2[b], sd);
         if (rc) break;
+        if (llr_bufs == 1) {  // the generator may overwrite the LLRs once they are planes; after the whole decode otherwise
+            if (!d->llr_free_recorded) CUDA_TRY(cudaEventRecord(d->ev_llr_free, sd));
+            CUDA_TRY(cudaStreamWaitEvent(sg, d->ev_llr_free, 0));
+        }
         const uint32_t* ref = per_frame_ref ? tmp.ref[b] : tmp.cws;  // nullptr = all-zero
         if (launch_count_all(wpf, n, d->cfg.k, nb, d->d_xhat2[b], ref, per_frame_ref ? 1 : 0, tmp.mask, tmp.cnt, d->num_sms, sd)) {
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(d->ev_out[b], sd));
             d->launches += 2;  // channel, counters
             continue;
+        }
+        // frames the one-pass kernels do not take (n < 32: a frame is part of one word; frames beyond the shared memory of an SM)
+        if (!tmp.diff) {  // x^ ^ x of a batch
+            CUDA_TRY(keep((void**)&d->d_ber_diff, &d->ber_diff_bytes, batch * (size_t)wpf * 4));
+            tmp.diff = d->d_ber_diff;
         }
         rc = scpd_count_errors(n, nb, d->d_xhat2[b], ref, per_frame_ref ? 1 : 0, (uint64_t*)tmp.cnt, sd);
         if (rc) break;

@@ -634,11 +634,12 @@ def test_run_ber_ex_codeword_cycle_and_random_payload(scpd):
     dec.close()
 
 
-@pytest.mark.parametrize("n", [8, 32, 256, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+@pytest.mark.parametrize("n", [8, 32, 256, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 524288])
 def test_run_ber_counters_and_transform_every_frame_size(scpd, n):
     """The ten counters of scpd_run_ber_ex and scpd_extract_info for every instantiation of the register-resident
-    kernels (count_all_kernel / polar_transform_reg_kernel: 1 ... 32 words per lane, fewer than 32 words per frame) and
-    for the sizes on either side that keep the multi-pass kernels (n < 32, n > 32768).  The decode is not what is
+    kernels (count_all_kernel / polar_transform_reg_kernel: 1 ... 32 words per lane, fewer than 32 words per frame), for
+    the shared-memory kernels of the frames above 32768 bits (with and without the opt-in above 48 KB) and for n < 32,
+    which keeps the multi-pass kernels.  The decode is not what is
     tested here (the product's own output is the input of the host counts): all-zero codeword, one stored codeword,
     random payloads, on a table that is not polar-structured, at a noise level that leaves errors in most frames."""
     import torch
@@ -646,7 +647,7 @@ def test_run_ber_counters_and_transform_every_frame_size(scpd, n):
     flags = (rng.random(n) < 0.5).astype(np.uint8)
     flags[-1] = 1
     k = int(flags.sum())
-    nfr, first, snr = (300 if n <= 4096 else 96), 1234567, 1.0
+    nfr, first, snr = (300 if n <= 4096 else 96 if n <= 65536 else 40), 1234567, 1.0
     dec = scpd.Decoder(n, k, flags, par=min(16, n // 2))
 
     def host_counts(x):  # x: None, [n] or [nfr, n]

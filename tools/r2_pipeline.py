@@ -4,10 +4,11 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import sc_polar_decoder_hls_b200 as scpd
-SETS = {"c1": ("FB_N1024_K512", 1024, 512, 2.5), "c2": ("frozen_n_4096_k_3072", 4096, 3072, 3.5)}
+SETS = {"c1": ("FB_N1024_K512", 1024, 512, 2.5), "c2": ("frozen_n_4096_k_3072", 4096, 3072, 3.5),
+        "c3": ("frozen_n_32768_k_29492_snr_4_5", 32768, 29492, 4.5), "c4": ("frozen_n_131072_k_117964", 131072, 117964, 4.5)}
 for key in sys.argv[1:] or ["c1", "c2"]:
     name, n, k, snr = SETS[key]
-    nfr = 1 << 20
+    nfr = min(1 << 20, (1 << 34) // n)
     llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -17,6 +18,8 @@ for key in sys.argv[1:] or ["c1", "c2"]:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
+    del llr
+    torch.cuda.empty_cache()
     dec = scpd.Decoder(n, k, scpd.packed_flags(name, n))
     dec.run_ber(snr, k / n, nfr)
     t0 = time.perf_counter()
