@@ -1122,7 +1122,6 @@ static int ensure_pipeline(scpd_decoder* d, size_t chunk, int llr_bufs = 2) {
         CUDA_TRY(cudaEventCreateWithFlags(&d->ev_llr_free, cudaEventDisableTiming));
     }
     if (chunk <= d->pipe_frames && llr_bufs <= d->pipe_llr_bufs) return SCPD_OK;
-    chunk = std::max(chunk, d->pipe_frames);
     for (int b = 0; b < 2; b++) {
         cudaFree(d->d_llr2[b]);
         cudaFree(d->d_xhat2[b]);

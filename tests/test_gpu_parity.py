@@ -634,6 +634,31 @@ def test_run_ber_ex_codeword_cycle_and_random_payload(scpd):
     dec.close()
 
 
+def test_run_ber_one_llr_buffer_for_large_trees(scpd):
+    """scpd_run_ber_ex on a large tree with more frames than one batch: ONE LLR staging buffer, refilled by the generator as
+    soon as the plane conversion of the previous batch is through, batches grown towards a full round and split evenly
+    (c3: 80 000 frames = 2 x 40 000).  The counters must equal the sum over the two halves run as single batches (the
+    path test_run_ber_counts pins on the oracle), also with per-frame references (random payloads), and the handle must
+    still serve scpd_decode_host (two staging buffers) and the loop again afterwards."""
+    name, n, k, snr = CONFIG_SETS["c3"]
+    flags = scpd.packed_flags(name, n)
+    nfr, first = 80000, 4321
+    for kw in ({}, {"random_payload": True, "payload_seed": 3}):
+        dec = scpd.Decoder(n, k, flags)  # a fresh handle: the first call of the handle is the one with one LLR buffer
+        whole = dec.run_ber_ex(snr, k / n, nfr, first_frame=first, **kw)
+        h1 = dec.run_ber_ex(snr, k / n, nfr // 2, first_frame=first, **kw)
+        h2 = dec.run_ber_ex(snr, k / n, nfr // 2, first_frame=first + nfr // 2, **kw)
+        assert whole == [a + b for a, b in zip(h1, h2)], kw
+        assert whole[3] == nfr and 0 < whole[1] < nfr and 0 < whole[7] <= whole[1]
+        dec.close()
+    dec = scpd.Decoder(n, k, flags)
+    assert dec.run_ber_ex(snr, k / n, nfr, first_frame=first, **kw) == whole
+    llr = _llrs(5, n, 40, k, 4.5)
+    assert (dec.decode_host(llr) == _oracle(n, 16, 8, 1, flags, llr)).all()
+    assert dec.run_ber_ex(snr, k / n, nfr, first_frame=first, **kw) == whole
+    dec.close()
+
+
 @pytest.mark.parametrize("n", [8, 32, 256, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 524288])
 def test_run_ber_counters_and_transform_every_frame_size(scpd, n):
     """The ten counters of scpd_run_ber_ex and scpd_extract_info for every instantiation of the register-resident
