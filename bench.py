@@ -11,7 +11,7 @@ A "step" is one scpd_decode() over the resident 4 GiB LLR batch (far larger than
   e2e      : the same through scpd_decode_host(): pinned host LLRs -> H2D -> decode -> D2H, every step
   configs  : (N = 1 only) the same device-resident measurement for all five BASELINE configs c1..c5, each with its own
              parity spot check against the oracle and both rooflines of SURVEY 8d (bytes at HBM peak, ops at the
-             measured integer-pipe peak)
+             measured integer-pipe peak); the large trees on whole rounds of the resident warps (see CONFIGS)
   pipeline : (N = 1 only) information Gb/s of the whole device Monte-Carlo loop scpd_run_ber (channel + decode + count)
   N > 1    : frames are sharded across ranks (one process per GPU, torchrun); no data-path collective,
              only a barrier and a max-reduction of the elapsed time ("weak" scaling).
