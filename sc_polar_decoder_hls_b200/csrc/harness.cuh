@@ -91,9 +91,22 @@ __device__ __forceinline__ int quantize_llr(float y) {  // sc_quantizer.h:77-80 
 // fast = 1: approximations only (a quantised LLR differs by one step on about 1e-5 of the samples).
 // FAST (the mode above) and CW (a codeword is given; otherwise all-zero: every symbol +1) are compile-time: the kernel is
 // bound by instruction issue, and the per-draw tests of run-time flags were a tenth of its instructions.
+// MUFU.LG2 / MUFU.RSQ without the denormal pre-scaling __logf / rsqrtf wrap around them (four instructions each): the
+// arguments here are r1 >= 2^-24 and t = -2 ln r1 >= 1.2e-7, or t = 0 for r1 = 1, which the guard sends to the libm-grade code
+__device__ __forceinline__ float lg2_approx_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int FAST, bool CW>
 __global__ void __launch_bounds__(128)
-channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nframes, uint32_t seed, float sigma,
+channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nframes, uint32_t seed, float sigma, float guard,
                const uint8_t* __restrict__ codeword, int per_frame, int8_t* __restrict__ llr, XsJumpTable jt, int log2c,
                uint32_t fpb /* frames per block */) {
     constexpr int fast = FAST;
@@ -125,7 +138,6 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
     const unsigned long long valid = (nframes - f0 < fpb ? nframes - f0 : (unsigned long long)fpb) * n;  // bytes of the block
     int8_t* out = llr + f0 * n;
     const float two_pi = __fmul_rn(2.0f, 3.14159265358979f);  // sc_awgn.h:61-62
-    const float guard = 2.5e-4f * fmaxf(sigma, 1.0f);
     const uint32_t nmask = n - 1u;
     const bool aligned = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
     // 16 bytes (8 draws) per store: a block is 32768 LLRs or one frame of more than that, so c >= 512 (the host checks)
@@ -141,8 +153,8 @@ channel_kernel(uint32_t n, unsigned long long first_frame, unsigned long long nf
             const float y = __fmul_rn(two_pi, r2);  // sc_awgn.h:67
             float x, sn, cs;
             if (fast) {
-                const float t = __fmul_rn(-2.0f, __logf(r1));
-                x = __fmul_rn(t, rsqrtf(t));
+                const float t = __fmul_rn(-1.3862943611198906f, lg2_approx_ftz(r1));  // -2 ln 2 * log2 r1
+                x = __fmul_rn(t, rsqrt_approx_ftz(t));
                 __sincosf(y, &sn, &cs);
             } else {
                 x = sqrtf(__fmul_rn(-2.0f, logf(r1)));  // :68

@@ -1392,8 +1392,9 @@ extern "C" int scpd_channel_generate(uint32_t n, uint64_t first_frame, size_t nf
     const unsigned long long nblk = (nframes + fpb - 1) / fpb;
     const unsigned grid = (unsigned)((nblk + 3) / 4);
     const int mode = channel_mode().load();
+    const float guard = 2.5e-4f * std::max(sigma, 1.0f);  // harness.cuh: distance from a quantiser bin edge below which a sample is recomputed
 #define SCPD_CHAN(M, C) \
-    channel_kernel<M, C><<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, d_codeword, per_frame, d_llr, jt, log2c, fpb)
+    channel_kernel<M, C><<<grid, 128, 0, (cudaStream_t)stream>>>(n, first_frame, nframes, seed, sigma, guard, d_codeword, per_frame, d_llr, jt, log2c, fpb)
     if (d_codeword) {
         if (mode == 0) SCPD_CHAN(0, true); else if (mode == 1) SCPD_CHAN(1, true); else SCPD_CHAN(2, true);
     } else {

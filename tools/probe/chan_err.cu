@@ -20,8 +20,11 @@ __global__ void probe(unsigned long long per_thread, float sigma, float r1_cut, 
         float sp, cp, sf, cf;
         const float xp = sqrtf(__fmul_rn(-2.0f, logf(r1)));
         sincosf(y, &sp, &cp);
-        const float t = __fmul_rn(-2.0f, __logf(r1));
-        const float xf = __fmul_rn(t, rsqrtf(t));
+        float l2, rs;  // the kernel's fast path (harness.cuh: lg2_approx_ftz, rsqrt_approx_ftz)
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(r1));
+        const float t = __fmul_rn(-1.3862943611198906f, l2);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
+        const float xf = __fmul_rn(t, rs);
         __sincosf(y, &sf, &cf);
         const float e0 = fabsf(4.0f * sigma * (xp * sp - xf * sf)), e1 = fabsf(4.0f * sigma * (xp * cp - xf * cf));
         const float e = fmaxf(e0, e1);
