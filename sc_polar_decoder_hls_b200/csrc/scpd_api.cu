@@ -1221,7 +1221,7 @@ extern "C" const char* scpd_last_kernel_name(const scpd_decoder* d) { return d ?
 
 // One CTA per frame with the frame in shared memory (N > 32768): grid and dynamic shared memory, 0 blocks = does not fit
 static unsigned smem_frame_grid(const void* kernel, uint32_t wpf, size_t nframes, int num_sms, size_t* smem) {
-    *smem = (size_t)wpf * 4;
+    *smem = ((size_t)wpf + 2) * 4;  // the frame, and two words for the sums of count_all_smem_kernel
     if (*smem > 200u * 1024u) return 0;
     if (*smem > 48u * 1024u && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess) {
         cudaGetLastError();

@@ -47,6 +47,9 @@ static inline uint32_t __brev(uint32_t v) {
     for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
     return r;
 }
+// the fibers of an emulated CTA run one at a time and switch only inside collectives: an atomic is a plain update
+template <class T, class U>
+static inline T atomicAdd(T* p, U v) { const T old = *p; *p = (T)(old + (T)v); return old; }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cuda_emu::collective_sync(); }
 // CTA barrier over the fibers of run_cta (kernels whose warps are emulated one after the other through run_warp
 // see a CTA of one warp and must not rely on cross-warp state under emulation)

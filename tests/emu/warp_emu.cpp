@@ -15,6 +15,10 @@
 #include "../../sc_polar_decoder_hls_b200/csrc/decode_bs.cuh"
 #include "../../sc_polar_decoder_hls_b200/csrc/decode_raw.cuh"
 #include "../../sc_polar_decoder_hls_b200/csrc/bs_plan.h"
+namespace scpd {
+uint32_t s_frame[32768 + 2];  // the dynamic shared memory of the counter kernels (count.cuh)
+}
+#include "../../sc_polar_decoder_hls_b200/csrc/count.cuh"
 
 namespace scpd {
 __attribute__((aligned(16))) uint8_t smem_fast[232448];
@@ -481,5 +485,66 @@ int emu_bs_prim(int fmt, int q, int op, size_t count, const uint8_t* sa, const u
         default: return -1;
     }
     return 0;
+}
+}  // extern "C"
+
+// ---- count.cuh under the emulator: counters and polar transform with the frame in registers (wpl = words per lane,
+// one of 1 2 4 8 16 32) or in shared memory (wpl = 0).  Returns 0, -1 for an unknown variant.
+namespace {
+struct CountArgs {
+    uint32_t wpf, n, k;
+    unsigned long long nframes;
+    const uint32_t *xhat, *ref, *mask;
+    int per_frame;
+    unsigned long long* counters;
+    uint32_t* uhat;
+};
+template <int WPL>
+void count_body(void* a) {
+    const CountArgs& c = *static_cast<CountArgs*>(a);
+    count_all_kernel<WPL>(c.wpf, c.n, c.k, c.nframes, c.xhat, c.ref, c.per_frame, c.mask, c.counters);
+}
+void count_smem_body(void* a) {
+    const CountArgs& c = *static_cast<CountArgs*>(a);
+    count_all_smem_kernel(c.wpf, c.n, c.k, c.nframes, c.xhat, c.ref, c.per_frame, c.mask, c.counters);
+}
+template <int WPL>
+void transform_body(void* a) {
+    const CountArgs& c = *static_cast<CountArgs*>(a);
+    polar_transform_reg_kernel<WPL>(c.wpf, c.nframes, c.xhat, c.uhat);
+}
+void transform_smem_body(void* a) {
+    const CountArgs& c = *static_cast<CountArgs*>(a);
+    polar_transform_smem_kernel(c.wpf, c.nframes, c.xhat, c.uhat);
+}
+int run_count_grid(void (*body)(void*), CountArgs* c, int grid, int warps) {
+    if (!body || warps > 8) return -1;
+    dim3 gd, bd;
+    gd.x = (unsigned)grid;
+    bd.x = (unsigned)warps * 32;
+    for (int b = 0; b < grid; b++) {
+        dim3 bi;
+        bi.x = (unsigned)b;
+        cuda_emu::run_cta(body, c, bi, gd, bd, 0, warps);
+    }
+    return 0;
+}
+}  // namespace
+extern "C" {
+int emu_count_all(int wpl, uint32_t wpf, uint32_t n, uint32_t k, unsigned long long nframes, const uint32_t* xhat,
+                  const uint32_t* ref, int per_frame, const uint32_t* mask, unsigned long long* counters, int grid) {
+    CountArgs c{wpf, n, k, nframes, xhat, ref, mask, per_frame, counters, nullptr};
+    void (*body)(void*) = wpl == 0 ? count_smem_body : wpl == 1 ? count_body<1> : wpl == 2 ? count_body<2> : wpl == 4 ? count_body<4>
+                          : wpl == 8 ? count_body<8> : wpl == 16 ? count_body<16> : wpl == 32 ? count_body<32> : nullptr;
+    if (wpl == 0 && wpf + 2 > sizeof(scpd::s_frame) / 4) return -2;
+    return run_count_grid(body, &c, grid, 8);
+}
+int emu_polar_transform(int wpl, uint32_t wpf, unsigned long long nframes, const uint32_t* xhat, uint32_t* uhat, int grid) {
+    CountArgs c{wpf, 0, 0, nframes, xhat, nullptr, nullptr, 0, nullptr, uhat};
+    void (*body)(void*) = wpl == 0 ? transform_smem_body : wpl == 1 ? transform_body<1> : wpl == 2 ? transform_body<2>
+                          : wpl == 4 ? transform_body<4> : wpl == 8 ? transform_body<8> : wpl == 16 ? transform_body<16>
+                          : wpl == 32 ? transform_body<32> : nullptr;
+    if (wpl == 0 && wpf + 2 > sizeof(scpd::s_frame) / 4) return -2;
+    return run_count_grid(body, &c, grid, 8);
 }
 }

@@ -349,3 +349,44 @@ def test_cooperative_fast_kernel_under_cta_emulator(w):
             assert (_cemu(w, flags, n, prune, llr, grid=2) == want).all(), (n, prune)
         ls = int(np.log2(n)) - 2
         assert (_cemu(w, flags, n, 2, llr, lsa=ls, lsb=ls - 1, grid=1) == want).all(), (n, "workspace")
+
+
+# (words per lane of the register kernels, or 0 for the shared-memory kernel; frame sizes that instantiation serves)
+_COUNT_VARIANTS = [(1, 32), (1, 256), (1, 1024), (2, 2048), (4, 4096), (8, 8192), (16, 16384), (32, 32768), (0, 1024), (0, 65536)]
+
+
+@pytest.mark.parametrize("wpl,n", _COUNT_VARIANTS)
+def test_counter_and_transform_kernels_under_warp_emulator(wpl, n):
+    """count.cuh executed on the CPU (tests/emu/warp_emu.cpp, a fiber per lane, eight warps per CTA): the ten counters of
+    the Monte-Carlo loop from one pass over x^ -- codeword bits as sc_error_counter.h:68-125 counts them (10-bit wrap
+    included), information bits through (x^ ^ x) F^(x)n -- and the transform alone, against the oracle's counter and
+    transform; all-zero, shared and per-frame references; frames with no, few and more than 1023 bit errors."""
+    rng = np.random.default_rng(1000 * wpl + n)
+    lib = _emu_lib('libwarp_emu.so')
+    wpf = n // 32
+    nfr = 21 if n <= 4096 else 5
+    flags = (rng.random(n) < 0.5).astype(np.uint8)
+    k = int(flags.sum())
+    mask = ol.pack_bits(flags[None, :])[0]
+    sent = rng.integers(0, 2, (nfr, n)).astype(np.uint8)
+    err = (rng.random((nfr, n)) < rng.choice([0.0, 2.0 / n, 0.3], size=(nfr, 1))).astype(np.uint8)
+    err[0] = 0
+    err[1] = 1  # every bit wrong: n errors, n & 1023 under the wrap
+    for mode in (0, 1, 2):  # all-zero codeword, one shared codeword, one per frame
+        x = np.zeros((nfr, n), np.uint8) if mode == 0 else np.broadcast_to(sent[0], (nfr, n)) if mode == 1 else sent
+        xhat = x ^ err
+        xw = np.ascontiguousarray(ol.pack_bits(xhat))
+        rw = None if mode == 0 else np.ascontiguousarray(ol.pack_bits(x[:1] if mode == 1 else x))
+        cnt = np.zeros(10, np.uint64)
+        rc = lib.emu_count_all(wpl, wpf, n, k, ctypes.c_ulonglong(nfr), ol.P(xw), ol.P(rw) if rw is not None else None,
+                               int(mode == 2), ol.P(mask), ol.P(cnt), 3)
+        assert rc == 0
+        e = ol.polar_transform(err)[:, flags == 1].sum(axis=1)
+        want = ol.count_errors(n, xhat, np.ascontiguousarray(x)) + [int(e.sum()), int((e != 0).sum()), nfr * k, nfr]
+        assert [int(v) for v in cnt] == want, (wpl, n, mode)
+    words = np.ascontiguousarray(ol.pack_bits(sent))
+    out = np.zeros_like(words)
+    assert lib.emu_polar_transform(wpl, wpf, ctypes.c_ulonglong(nfr), ol.P(words), ol.P(out), 2) == 0
+    assert (out == ol.pack_bits(ol.polar_transform(sent))).all()
+    assert lib.emu_polar_transform(wpl, wpf, ctypes.c_ulonglong(nfr), ol.P(out), ol.P(out), 2) == 0  # in place; an involution
+    assert (out == words).all()
