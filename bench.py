@@ -38,9 +38,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # BASELINE.json configs: table, N, K, Eb/N0, frames per step of the device-resident measurement.  The large
 # trees are measured on whole rounds of the resident warps (148 SMs x 16 warps x 32 frames = 75 776 frames a round:
-# c3 two rounds, c4 one, c5 2^16 frames = 2048 of the 2368 warps; `profiles/tuning_r2.md` "Batches in whole rounds").
+# c1 fourteen rounds (1 060 864 frames; 2^20 would be 13.84), c3 two rounds, c4 one, c5 2^16 frames = 2048 of the 2368 warps; `profiles/tuning_r2.md` "Batches in whole rounds").
 CONFIGS = {
-    "c1": dict(name="FB_N1024_K512", n=1024, k=512, ebn0=2.5, frames=1 << 20, check=256),
+    "c1": dict(name="FB_N1024_K512", n=1024, k=512, ebn0=2.5, frames=14 * 75776, check=256),
     "c2": dict(name="frozen_n_4096_k_3072", n=4096, k=3072, ebn0=3.5, frames=1 << 20, check=256),
     "c3": dict(name="frozen_n_32768_k_29492_snr_4_5", n=32768, k=29492, ebn0=4.5, frames=151552, check=64),
     "c4": dict(name="frozen_n_131072_k_117964", n=131072, k=117964, ebn0=4.5, frames=75776, check=16),
