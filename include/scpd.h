@@ -163,6 +163,11 @@ int scpd_stage_profile(const scpd_config* cfg, const uint8_t* h_info_flags, scpd
  * scpd_stage_time reads and clears the histogram.  SCPD_E_UNSUPPORTED for handles without that kernel. */
 int scpd_stage_timing(scpd_decoder* d, int enable);
 int scpd_stage_time(scpd_decoder* d, uint64_t cycles[6][32], uint64_t visits[6][32]);
+/* With the same switch on: how often the profiled warps reached an all-information (R1) node of 2^l LLRs and how often a
+ * zero LLR in one of the warp's 32 frames sent the node to the full walk instead of the hard-decision shortcut (CA2:
+ * hd(0) = 0 whatever the sign bit says, functions.h:48-70 / SURVEY G3).  What scpd_schedule_stats reports as pruned is
+ * the best case; this is the measured share.  Reads and clears. */
+int scpd_r1_votes(scpd_decoder* d, uint64_t votes[32], uint64_t fallbacks[32]);
 
 /* ---- testbench harness on the device: src/testbench/ ---- */
 /* sigma = 1/sqrt(2 R 10^(EbN0/10)), main.cpp:91-98 (the reference hard-codes R = 0.5). */

@@ -79,6 +79,7 @@ def _load():
                                       c.c_uint64, c.POINTER(c.c_uint64)]),
         "scpd_stage_timing": (c.c_int, [vp, c.c_int]),
         "scpd_stage_time": (c.c_int, [vp, vp, vp]),
+        "scpd_r1_votes": (c.c_int, [vp, vp, vp]),
         "scpd_last_error": (c.c_char_p, []),
         "scpd_status_string": (c.c_char_p, [c.c_int]),
     }
@@ -95,7 +96,7 @@ EXPORTS = ["scpd_frozen_load_order", "scpd_frozen_load_flags", "scpd_frozen_writ
            "scpd_decode", "scpd_decode_host", "scpd_validate_llr", "scpd_extract_info", "scpd_get_config",
            "scpd_schedule_stats", "scpd_launch_count", "scpd_kernel_timing", "scpd_last_kernel_ms",
            "scpd_kernel_name", "scpd_last_kernel_name", "scpd_stage_profile", "scpd_sigma", "scpd_channel_generate", "scpd_channel_mode",
-           "scpd_count_errors", "scpd_run_ber", "scpd_run_ber_ex", "scpd_stage_timing", "scpd_stage_time", "scpd_last_error",
+           "scpd_count_errors", "scpd_run_ber", "scpd_run_ber_ex", "scpd_stage_timing", "scpd_stage_time", "scpd_r1_votes", "scpd_last_error",
            "scpd_status_string"]
 SRC_CODEWORDS, SRC_RANDOM = 0, 1
 
@@ -273,6 +274,12 @@ class Decoder:
 
     def stage_timing(self, enable=True):
         check(lib.scpd_stage_timing(self._h, 1 if enable else 0))
+
+    def r1_votes(self):
+        """(votes, fallbacks): uint64 [32] per log2 node size since the last call (scpd_r1_votes; stage timing on)."""
+        v, f = np.zeros(32, np.uint64), np.zeros(32, np.uint64)
+        check(lib.scpd_r1_votes(self._h, _np_ptr(v), _np_ptr(f)))
+        return v, f
 
     def stage_time(self):
         """(cycles, visits): uint64 [6, 32] per (function, level) since the last call (scpd_stage_time)."""

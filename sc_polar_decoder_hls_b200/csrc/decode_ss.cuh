@@ -772,6 +772,19 @@ struct SsThread {
         return (l == p.ltm && !in_planes(l, wd)) ? op_hd_x<true>(l, wd) : op_hd_x<false>(l, wd);
     }
 
+    // PROF build only: how often the R1 shortcut (hard decision = sign) is voted on at nodes of 2^l LLRs and how often a
+    // zero LLR somewhere in the warp sends the node to the full walk instead (scpd_r1_votes; profiled warps only)
+    SS_DEV void prof_vote(uint32_t l, bool fallback) {
+#if defined(__CUDA_ARCH__)
+        if (PROF && prof_on && (threadIdx.x & 31u) == 0u) {
+            atomicAdd(p.prof + 384u + l, 1ull);
+            if (fallback) atomicAdd(p.prof + 416u + l, 1ull);
+        }
+#else
+        (void)l;
+        (void)fallback;
+#endif
+    }
     // ---------------------------------------------------------------- nodes of 64 and 32 LLRs
     // a, b: the two chunks of alpha[6] (also stored at aptr(6) when the node needs them again for g)
     // d0: node types (64, left 32, right 32) + kind + pruning flag; d1: the 64 flags' low word, d2: high word,
@@ -786,6 +799,7 @@ struct SsThread {
                 *reinterpret_cast<uint2*>(bword(6, wd)) = make_uint2(a.s, b.s);
                 walk = false;
             }
+            prof_vote(6u, walk);
         }
         if (walk) {
             // both children in one loop that is not unrolled: the 32-LLR walker (plane -> fp16x2 conversion, walk32, sign-bit
@@ -812,6 +826,7 @@ struct SsThread {
                 if (ts == SS_T_R1) {
                     const uint32_t nz = bs::nonzero<P>(r);
                     hard = !SS_ANY(~nz != 0u);  // no zero anywhere in the warp: hd = sign
+                    prof_vote(5u, !hard);
                 }
                 if (hard) {
                     bits = r.s;
@@ -916,6 +931,7 @@ struct SsThread {
                     break;
                 case SS_R1: {
                     const bool z = op_hd(l, wd);
+                    prof_vote(l, z);
                     pc += 2u + (z ? 0u : sched[pc + 1]);
                     break;
                 }

@@ -178,7 +178,7 @@ struct scpd_decoder {
     size_t ss_ws_bytes = 0;
     uint4* d_ss_planes = nullptr;
     size_t ss_planes_bytes = 0;
-    unsigned long long* d_ss_prof = nullptr;  // scpd_stage_timing: [2][6][32] cycles / visits
+    unsigned long long* d_ss_prof = nullptr;  // scpd_stage_timing: [2][6][32] cycles / visits, then [2][32] R1 votes / fallbacks
     // raw-pattern kernel plan (decode_raw.cuh): the configurations outside the in-range int16x2 / bit-sliced
     // datapaths.  raw_only: it is the only kernel of this handle
     bool raw_ok = false, raw_only = false;
@@ -1295,8 +1295,8 @@ extern "C" int scpd_stage_timing(scpd_decoder* d, int enable) {
     CUDA_TRY(cudaFuncSetAttribute((const void*)kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
     if (enable && !d->d_ss_prof) {
-        CUDA_TRY(cudaMalloc(&d->d_ss_prof, 2 * 6 * 32 * sizeof(unsigned long long)));
-        CUDA_TRY(cudaMemset(d->d_ss_prof, 0, 2 * 6 * 32 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&d->d_ss_prof, (2 * 6 + 2) * 32 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(d->d_ss_prof, 0, (2 * 6 + 2) * 32 * sizeof(unsigned long long)));
     } else if (!enable && d->d_ss_prof) {
         cudaFree(d->d_ss_prof);
         d->d_ss_prof = nullptr;
@@ -1316,6 +1316,24 @@ extern "C" int scpd_stage_time(scpd_decoder* d, uint64_t cycles[6][32], uint64_t
             cycles[f][l] = h[f * 32 + l];
             visits[f][l] = h[192 + f * 32 + l];
         }
+    return SCPD_OK;
+}
+
+// R1 shortcut statistics of the profiled warps since the last call (the PROF build of the slot-sliced kernel): votes[l] =
+// R1 nodes of 2^l LLRs reached (l = 5: 32-LLR children, 6: 64-LLR nodes, above: SS_R1 ops), fallbacks[l] = those that a zero
+// LLR somewhere in the warp's 32 frames sent to the full walk instead (CA2: hd(0) = 0 whatever the sign)
+extern "C" int scpd_r1_votes(scpd_decoder* d, uint64_t votes[32], uint64_t fallbacks[32]) {
+    if (!d || !votes || !fallbacks) return set_error(SCPD_E_ARG, "scpd_r1_votes: null argument");
+    if (!d->d_ss_prof) return set_error(SCPD_E_ARG, "scpd_r1_votes: timing is off (scpd_stage_timing)");
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long h[64];
+    CUDA_TRY(cudaMemcpy(h, d->d_ss_prof + 384, sizeof h, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(d->d_ss_prof + 384, 0, sizeof h));
+    for (int l = 0; l < 32; l++) {
+        votes[l] = h[l];
+        fallbacks[l] = h[32 + l];
+    }
     return SCPD_OK;
 }
 

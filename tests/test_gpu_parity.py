@@ -725,6 +725,33 @@ def test_stage_time_matrix(scpd):
     dec.close()
 
 
+def test_r1_votes_count_the_zero_llr_fallbacks(scpd):
+    """scpd_r1_votes: the measured side of the pruning statistics.  Every R1 node the profiled warps reach is a vote; a
+    zero LLR in any of the warp's 32 frames turns it into a fallback (full walk).  LLRs without a zero: no fallback; all-zero
+    LLRs: every vote falls back; channel LLRs (trunc(4 y) is 0 for |y| < 0.25): somewhere in between, and the same bits."""
+    import torch
+    name, n, k, snr = CONFIG_SETS["c1"]
+    flags = scpd.packed_flags(name, n)
+    dec = scpd.Decoder(n, k, flags)
+    nfr = 148 * 16 * 32
+    llr = scpd.channel_generate(n, nfr, scpd.sigma(snr, k / n))
+    want = dec.decode(llr).clone()
+    dec.stage_timing(True)
+    shares = []
+    for x in (torch.where(llr == 0, torch.ones_like(llr), llr), torch.zeros_like(llr), llr):
+        got = dec.decode(x)
+        torch.cuda.synchronize()
+        v, f = dec.r1_votes()
+        assert v.sum() > 0 and (f <= v).all() and v[:5].sum() == 0
+        shares.append(float(f.sum()) / float(v.sum()))
+    assert torch.equal(got, want)  # the profiled build decodes the same bits
+    assert shares[0] == 0.0 and shares[1] == 1.0 and 0.0 < shares[2] < 1.0
+    v, f = dec.r1_votes()
+    assert v.sum() == 0 and f.sum() == 0  # read clears
+    dec.stage_timing(False)
+    dec.close()
+
+
 def test_extract_info_and_roundtrip_full_size(scpd):
     """Size-independent property at BASELINE scale (c2, 2^17 frames = 512 MiB of LLRs): random
     information words -> polar transform -> noiseless LLRs -> decode returns the codeword, and
